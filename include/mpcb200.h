@@ -1,0 +1,120 @@
+/* mpcb200.h -- C ABI of libmpcb200.so: batched nonlinear-MPC solves on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of TGoldC/Motion-Planning-for-Autonomous-Driving-with-MPC:
+ * the per-MPC-step NLP solve that `CasadiOptimizer.optimize()` performs with
+ *     sol, f = self.solver();  res = sol(x0=init_control, p=c_p, lbg=..., lbx=..., ubg=..., ubx=...)
+ * (/root/reference/MPC_Planner/optimizer.py:605-607), plus the two tiny host steps either side of it
+ * (`shift_movement` :645-655, `desired_command_and_trajectory` :657-702) so that a closed loop can stay on the device.
+ *
+ * Plain pointers and sizes only; every `d_` pointer is a DEVICE pointer (e.g. torch.Tensor.data_ptr()), every
+ * `h_` pointer is a HOST pointer.  All calls are asynchronous on the given CUDA stream unless stated.  Return value:
+ * 0 on success, negative on an API / CUDA error (text via mpcb200_last_error).  Per-problem solver outcome goes to
+ * `d_status[B]` using the Forcespro exit codes the reference already knows (test/FORCESNLPsolver/include/
+ * FORCESNLPsolver.h:70-106): 1 optimal, 0 iteration limit, -6 NaN, -7 no progress; additionally -8 = the pinned
+ * stage X_0 violates a constraint (IPOPT would report an infeasible problem).  The batch is never aborted
+ * (contrast optimizer.py:330).
+ *
+ * Array layouts (row-major, float64 like the reference's numpy arrays; arithmetic precision is cfg.precision):
+ *     xref  [B][N+1][5]   the reference's X_ref parameter block: row 0 = current state (pinned X_0), rows 1..N =
+ *                         [path_x, path_y, 0, v_des, orientation]            (optimizer.py:600, 667-699)
+ *     X     [B][N+1][5]   in: state warm start / out: optimal states          (optimizer.py:602, 617)
+ *     U     [B][N][2]     in: control warm start / out: optimal controls      (optimizer.py:602, 616)
+ *   state = [sx, sy, delta, v, psi], control = [delta_dot, a]                 (configuration.py:354-368)
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB200_ABI_VERSION 1
+
+enum { MPCB200_F32 = 0, MPCB200_F64 = 1 };
+enum { MPCB200_HESS_GAUSS_NEWTON = 0, MPCB200_HESS_EXACT = 1 };
+
+/* Everything `Optimizer.__init__` pulls out of `configuration` (optimizer.py:34-68) + solver options.
+ * Replaces: the Python attributes of Optimizer, the lbg/ubg/lbx/ubx lists of inequal_constraints (optimizer.py:413-491)
+ * and the IPOPT option dict (optimizer.py:556). */
+typedef struct mpcb200_config {
+  int32_t abi_version;      /* = MPCB200_ABI_VERSION */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t N;                /* predict_horizon (optimizer.py:56) */
+  int32_t max_batch;        /* largest B a call will pass */
+  int32_t precision;        /* MPCB200_F32 | MPCB200_F64 : arithmetic type of the kernels */
+  int32_t hessian;          /* MPCB200_HESS_GAUSS_NEWTON | MPCB200_HESS_EXACT */
+  int32_t max_iter;         /* SQP iteration limit per solve (ipopt.max_iter = 100, optimizer.py:556) */
+  int32_t ls_max;           /* line-search trial limit */
+  double dt;                /* configuration.delta_t */
+  double l_wb;              /* p.a + p.b = 2.5789128 (configuration.py:362-363) */
+  double l_fric;            /* 2.578, literal of the friction row (optimizer.py:378) */
+  double Q[5];              /* weight_x, weight_y, weight_steering_angle, weight_velocity, weight_heading_angle */
+  double R[2];              /* weight_velocity_steering_angle, weight_long_acceleration (optimizer.py:500-504) */
+  double deltav_min, deltav_max;   /* optimizer.py:40-41 */
+  double a_max;                    /* optimizer.py:46 */
+  double delta_min, delta_max;     /* optimizer.py:37-38 */
+  double v_min, v_max;             /* optimizer.py:43-44 */
+  double r_sum;             /* radius_ego + radius_obstacle (optimizer.py:439) */
+  double ego_offset;        /* ego circle-centre offset along heading, 0.75 m (configuration.py:80-91) */
+  double obstacle[6];       /* obstacle circle centres: centre, front, rear (optimizer.py:60-64) */
+  double mu0, mu_min, mu_factor;   /* barrier schedule */
+  double tol_step, tol_feas;       /* convergence: inf-norm of the Newton step, l1 norm of the defects */
+  double tau_min, bound_push;      /* fraction-to-the-boundary, initial interior push */
+} mpcb200_config;
+
+typedef struct mpcb200_handle mpcb200_handle;
+
+/* Fill `cfg` with the reference's constants (vehicle 2 bounds, IPOPT-like tolerances for the chosen precision). */
+void mpcb200_default_config(mpcb200_config* cfg, int32_t N, int32_t precision);
+
+/* Create / destroy a solver handle (owns only its scratch). One handle per stream/GPU; not thread-safe. */
+int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out);
+void mpcb200_destroy(mpcb200_handle* h);
+const char* mpcb200_last_error(const mpcb200_handle* h);   /* h may be NULL: error of the last failed create */
+
+/* Replaces optimizer.py:605-607 for B independent ego instances: one fused kernel runs ALL SQP iterations of its
+ * problems (each lane iterates until its own problem converges).  d_iters/d_status may be NULL. */
+int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U,
+                  int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
+
+/* Same solve, one kernel launch per SQP iteration with the per-problem KKT slab (iterate, multipliers, slacks,
+ * Riccati blocks) staged HBM -> shared memory by TMA bulk copy and written back each launch:
+ *   begin: load problem data, initialise;  iter: `n_iter` iterations per call;  end: write X, U, status, iters. */
+int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X, const double* d_U, int32_t B, void* cuda_stream);
+int mpcb200_sqp_iter(mpcb200_handle* h, int32_t n_iter, void* cuda_stream);
+int mpcb200_sqp_end(mpcb200_handle* h, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters, void* cuda_stream);
+
+/* shift_movement (optimizer.py:645-655): x+ = x + dt*f(x, U[:,0]); shift U and X one stage, repeating the last.
+ * d_x [B][5] in/out (current state), d_U/d_X in/out, d_u_applied [B][2] out (may be NULL). */
+int mpcb200_plant_step_shift(mpcb200_handle* h, double* d_x, double* d_U, double* d_X, double* d_u_applied,
+                             int32_t B, void* cuda_stream);
+
+/* desired_command_and_trajectory (optimizer.py:657-702): build X_ref for MPC step `i` from the resampled path.
+ * d_path [T][2], d_orientation [T], d_x [B][5] current states -> d_xref [B][N+1][5]. */
+int mpcb200_build_ref_window(mpcb200_handle* h, int32_t i, int32_t iter_length, const double* d_path,
+                             const double* d_orientation, double desired_velocity, const double* d_x,
+                             double* d_xref, int32_t B, void* cuda_stream);
+
+/* The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631) on the device, no host
+ * sync between MPC steps: for i in 0..iter_length-1: solve, record u_0, plant step + shift, next window.
+ * d_x0 [B][5]; outputs d_traj [B][iter_length][5] (Q12: x0 first, last dropped), d_ctrl [B][iter_length][2],
+ * d_status [B][iter_length], d_iters [B][iter_length] (may be NULL). */
+int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_path, const double* d_orientation,
+                        double desired_velocity, const double* d_x0, double* d_traj, double* d_ctrl,
+                        int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
+
+/* Host-buffer convenience used by the end-to-end path: H2D of xref/X/U, solve, D2H of X/U/status/iters, synchronous. */
+int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, double* h_U,
+                       int32_t* h_status, int32_t* h_iters, int32_t B);
+
+/* Introspection for benches/tests. */
+int64_t mpcb200_launch_count(const mpcb200_handle* h);       /* kernels launched by this handle so far */
+int32_t mpcb200_workspace_words(const mpcb200_handle* h);    /* words of the per-problem KKT slab */
+int32_t mpcb200_slab_in_smem(const mpcb200_handle* h);       /* 1 if the slab lives in shared memory */
+int32_t mpcb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H */

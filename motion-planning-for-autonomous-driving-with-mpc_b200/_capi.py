@@ -1,0 +1,114 @@
+"""ctypes binding of libmpcb200.so (include/mpcb200.h).  No torch types cross this boundary: device pointers are
+passed as integers (`tensor.data_ptr()`), the stream as `torch.cuda.current_stream().cuda_stream`.
+
+There is NO CPU fallback: if the library is missing or CUDA is unavailable, loading/creating raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpcb200.so")
+
+F32, F64 = 0, 1
+HESS_GAUSS_NEWTON, HESS_EXACT = 0, 1
+ABI_VERSION = 1
+
+# status codes (mirror test/FORCESNLPsolver/include/FORCESNLPsolver.h:70-106)
+ST_OPTIMAL, ST_MAXIT, ST_NAN, ST_NOPROGRESS, ST_INFEASIBLE_X0 = 1, 0, -6, -7, -8
+
+
+class Config(C.Structure):
+    """mpcb200_config"""
+    _fields_ = ([(n, C.c_int32) for n in ("abi_version", "device", "N", "max_batch", "precision", "hessian",
+                                          "max_iter", "ls_max")] +
+                [("dt", C.c_double), ("l_wb", C.c_double), ("l_fric", C.c_double), ("Q", C.c_double * 5),
+                 ("R", C.c_double * 2), ("deltav_min", C.c_double), ("deltav_max", C.c_double), ("a_max", C.c_double),
+                 ("delta_min", C.c_double), ("delta_max", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double),
+                 ("r_sum", C.c_double), ("ego_offset", C.c_double), ("obstacle", C.c_double * 6),
+                 ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_factor", C.c_double), ("tol_step", C.c_double),
+                 ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double)])
+
+
+EXPORTS = {
+    "mpcb200_default_config": (None, [C.POINTER(Config), C.c_int32, C.c_int32]),
+    "mpcb200_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "mpcb200_destroy": (None, [C.c_void_p]),
+    "mpcb200_last_error": (C.c_char_p, [C.c_void_p]),
+    "mpcb200_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_sqp_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_sqp_iter": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_sqp_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpcb200_plant_step_shift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_build_ref_window": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "mpcb200_launch_count": (C.c_int64, [C.c_void_p]),
+    "mpcb200_workspace_words": (C.c_int32, [C.c_void_p]),
+    "mpcb200_slab_in_smem": (C.c_int32, [C.c_void_p]),
+    "mpcb200_abi_version": (C.c_int32, []),
+}
+
+_lib = None
+
+
+class Mpcb200Error(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libmpcb200.so and type every export declared in include/mpcb200.h.  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Mpcb200Error(f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.mpcb200_abi_version() != ABI_VERSION:
+            raise Mpcb200Error("libmpcb200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def default_config(N, precision=F32):
+    cfg = Config()
+    load().mpcb200_default_config(C.byref(cfg), N, precision)
+    return cfg
+
+
+class Handle:
+    """RAII wrapper of mpcb200_handle."""
+
+    def __init__(self, cfg):
+        self.lib = load()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.mpcb200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            msg = self.lib.mpcb200_last_error(None)
+            raise Mpcb200Error(f"mpcb200_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.mpcb200_last_error(self.h)
+            raise Mpcb200Error(f"libmpcb200 call failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpcb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mpcb200_launch_count(self.h))

@@ -1,0 +1,40 @@
+// config_params.h -- mpcb200_config (C ABI) -> ParamsT<T> (kernel constants), plus the defaults.
+#pragma once
+#include "../../include/mpcb200.h"
+#include "sqp_core.cuh"
+
+namespace mpcb200 {
+
+template <typename T>
+inline ParamsT<T> params_from_config(const mpcb200_config& c) {
+  ParamsT<T> p;
+  p.N = c.N; p.max_iter = c.max_iter; p.hessian = c.hessian; p.ls_max = c.ls_max;
+  p.dt = (T)c.dt; p.l_wb = (T)c.l_wb; p.l_fric = (T)c.l_fric;
+  for (int i = 0; i < 5; ++i) p.Q[i] = (T)c.Q[i];
+  for (int i = 0; i < 2; ++i) p.R[i] = (T)c.R[i];
+  p.dd_min = (T)c.deltav_min; p.dd_max = (T)c.deltav_max; p.a_max = (T)c.a_max;
+  p.de_min = (T)c.delta_min; p.de_max = (T)c.delta_max; p.v_min = (T)c.v_min; p.v_max = (T)c.v_max;
+  p.r_sum = (T)c.r_sum; p.ego_off = (T)c.ego_offset;
+  p.mu0 = (T)c.mu0; p.mu_min = (T)c.mu_min; p.mu_factor = (T)c.mu_factor;
+  p.tol_step = (T)c.tol_step; p.tol_feas = (T)c.tol_feas; p.tau_min = (T)c.tau_min; p.bound_push = (T)c.bound_push;
+  return p;
+}
+
+inline void default_config(mpcb200_config* c, int N, int precision) {
+  c->abi_version = MPCB200_ABI_VERSION; c->device = 0; c->N = N; c->max_batch = 4096;
+  c->precision = precision; c->hessian = MPCB200_HESS_EXACT; c->max_iter = 100; c->ls_max = 8;
+  c->dt = 0.1; c->l_wb = 2.5789128; c->l_fric = 2.578;
+  const double Q[5] = {2.3, 2.3, 500.0, 0.1, 10.0}, R[2] = {2.0, 0.2};   // config_LF_ZAM_Over-1_1.yaml:19-31
+  for (int i = 0; i < 5; ++i) c->Q[i] = Q[i];
+  for (int i = 0; i < 2; ++i) c->R[i] = R[i];
+  c->deltav_min = -0.4; c->deltav_max = 0.4; c->a_max = 11.5; c->delta_min = -1.066; c->delta_max = 1.066;
+  c->v_min = 0.0; c->v_max = 50.8;
+  c->r_sum = 1.2; c->ego_offset = 0.75;                                    // lane following: dummy obstacle (Q11)
+  const double ob[6] = {-100.0, 0.0, -100.0, 0.0, -100.0, 0.0};
+  for (int i = 0; i < 6; ++i) c->obstacle[i] = ob[i];
+  c->mu0 = 0.1; c->mu_factor = 0.2; c->tau_min = 0.99; c->bound_push = 1e-2;
+  if (precision == MPCB200_F64) { c->mu_min = 1e-9; c->tol_step = 1e-8; c->tol_feas = 1e-8; }
+  else                          { c->mu_min = 1e-6; c->tol_step = 2e-5; c->tol_feas = 1e-4; }
+}
+
+}  // namespace mpcb200

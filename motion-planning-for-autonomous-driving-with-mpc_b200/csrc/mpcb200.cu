@@ -1,0 +1,596 @@
+// mpcb200.cu -- sm_100a kernels + the C ABI of libmpcb200.so (include/mpcb200.h).
+//
+// Execution model (B200-first, not a translation of anything in the reference -- the reference has no GPU code):
+//   * one ego instance (one NLP) per CUDA lane; a CTA is ONE warp that owns a tile of LANES problems;
+//   * the tile's whole KKT working set ("slab": iterate, reference, multipliers, slacks, Riccati gains, step) lives in
+//     shared memory as [word][lane] so every access is bank-conflict free; it is 1303 words/problem at N = 30;
+//   * problem data moves HBM <-> shared memory with TMA bulk copies (cp.async.bulk + mbarrier): the tile's float64
+//     xref/X/U rows are one contiguous chunk each (one bulk load per array, one bulk store per output array), and in
+//     the launch-per-iteration mode the slab itself is one bulk load + one bulk store per launch;
+//   * all SQP iterations of a problem run inside one launch (problems are independent, so no grid-wide sync is ever
+//     needed); lanes that converge early idle until their warp is done;
+//   * up to 148 x (227 KB / slab) tiles are co-resident; larger batches run in waves.
+// Tensor cores are not used: the factorisation works on 5x5/2x2 stage blocks along a length-N dependency chain.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <new>
+
+#include "config_params.h"
+
+using namespace mpcb200;
+
+// ===================================================================================================== PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk-group completion)
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ===================================================================================================== kernel args
+enum : int { MODE_ONESHOT = 0, MODE_BEGIN = 1, MODE_ITER = 2, MODE_END = 3 };
+
+template <typename T>
+struct SolveArgs {
+  ParamsT<T> P;
+  double obstacle[6];
+  const double* xref;   // [B][N+1][5]
+  double* X;            // [B][N+1][5]
+  double* U;            // [B][N][2]
+  int* status;          // [B]
+  int* iters;           // [B]
+  T* slab;              // global image of the slabs [tiles][words][LANES] (stepwise mode / global-workspace mode)
+  ProbState<T>* state;  // [B] (stepwise mode)
+  T* obs_shift;         // [B][6] shifted obstacle centres (stepwise mode)
+  int B;
+  int mode;
+  int n_iter;
+};
+
+// cooperative tile copy HBM <-> staging: one TMA bulk op for a full tile, per-lane loops for a ragged last tile
+template <int LANES>
+__device__ __forceinline__ void tile_load(double* sdst, const double* gsrc, int per_problem, int nvalid, uint64_t* bar, uint32_t& phase) {
+  const int lane = threadIdx.x;
+  if (nvalid == LANES) {
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(LANES * per_problem * sizeof(double));
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(sdst, gsrc, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = lane; i < nvalid * per_problem; i += 32) sdst[i] = gsrc[i];
+    __syncwarp();
+  }
+}
+template <int LANES>
+__device__ __forceinline__ void tile_store(double* gdst, const double* ssrc, int per_problem, int nvalid) {
+  const int lane = threadIdx.x;
+  __syncwarp();
+  if (nvalid == LANES) {
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_1d(gdst, ssrc, (uint32_t)(LANES * per_problem * sizeof(double)));
+      tma_store_commit_wait();
+    }
+    __syncwarp();
+  } else {
+    for (int i = lane; i < nvalid * per_problem; i += 32) gdst[i] = ssrc[i];
+    __syncwarp();
+  }
+}
+
+// ===================================================================================================== solve kernel
+// SMEM_WS: slab in shared memory (staging aliases the K/V/S/TR block, dead during load/store); otherwise the slab is
+// the global image and shared memory only holds the float64 staging.
+template <typename T, int LANES, bool SMEM_WS>
+__global__ void __launch_bounds__(32, 1) mpc_solve_kernel(const SolveArgs<T> a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int N = a.P.N;
+  const Layout L(N);
+  const int base = tile * LANES;
+  const int nvalid = min(LANES, a.B - base);
+  const bool valid = lane < nvalid;
+  const int b = base + (valid ? lane : 0);
+
+  T* slab_s = reinterpret_cast<T*>(smem_raw);
+  T* slab_g = a.slab ? a.slab + (size_t)tile * L.words * LANES : nullptr;
+  T* wsbase = SMEM_WS ? slab_s : slab_g;
+  double* stage = SMEM_WS ? reinterpret_cast<double*>(slab_s + (size_t)L.o_K * LANES) : reinterpret_cast<double*>(smem_raw);
+  const int nx = 5 * (N + 1), nu = 2 * N;
+  double* st_xref = stage;
+  double* st_X = stage + (size_t)LANES * nx;
+  double* st_U = st_X + (size_t)LANES * nx;
+
+  uint32_t phase = 0;
+  if (lane == 0) mbar_init(&bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  Ws<T, LANES> ws{wsbase + (lane < LANES ? lane : 0)};
+  T obs[6];
+  Solver<T, LANES> S(a.P, ws, obs);
+  ProbState<T> st;
+
+  if (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN) {
+    tile_load<LANES>(st_xref, a.xref + (size_t)base * nx, nx, nvalid, &bar, phase);
+    tile_load<LANES>(st_X, a.X + (size_t)base * nx, nx, nvalid, &bar, phase);
+    tile_load<LANES>(st_U, a.U + (size_t)base * nu, nu, nvalid, &bar, phase);
+    if (valid) {
+      S.load(st_xref + (size_t)lane * nx, st_X + (size_t)lane * nx, st_U + (size_t)lane * nu, a.obstacle, obs);
+    }
+    __syncwarp();   // staging is dead from here; init() overwrites the aliased V/S block
+    if (valid) S.init(st); else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
+  } else {
+    // resume: bring the slab image back (TMA bulk) and the per-problem scalars
+    if (SMEM_WS) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)((size_t)L.words * LANES * sizeof(T));
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(slab_s, slab_g, bytes, &bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+    }
+    if (valid) {
+      st = a.state[b];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) obs[j] = a.obs_shift[(size_t)b * 6 + j];
+    } else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
+  }
+
+  if (a.mode != MODE_END) {
+    for (int it = 0; it < a.n_iter; ++it) {
+      if (__all_sync(0xffffffffu, st.done)) break;
+      if (!st.done) S.iterate(st);
+    }
+  }
+
+  if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
+    // solution back to float64 row-major: staging needs xref again (rho is added back in float64)
+    __syncwarp();
+    tile_load<LANES>(st_xref, a.xref + (size_t)base * nx, nx, nvalid, &bar, phase);
+    if (valid) S.store(st_xref + (size_t)lane * nx, st_X + (size_t)lane * nx, st_U + (size_t)lane * nu);
+    tile_store<LANES>(a.X + (size_t)base * nx, st_X, nx, nvalid);
+    tile_store<LANES>(a.U + (size_t)base * nu, st_U, nu, nvalid);
+    if (valid) {
+      if (a.status) a.status[b] = st.status;
+      if (a.iters) a.iters[b] = st.iters;
+    }
+  } else {
+    // keep the slab + scalars for the next launch
+    if (SMEM_WS) {
+      __syncwarp();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_1d(slab_g, slab_s, (uint32_t)((size_t)L.words * LANES * sizeof(T)));
+        tma_store_commit_wait();
+      }
+      __syncwarp();
+    }
+    if (valid) {
+      a.state[b] = st;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a.obs_shift[(size_t)b * 6 + j] = obs[j];
+    }
+  }
+}
+
+// ===================================================================================================== closed loop
+template <typename T>
+struct LoopArgs {
+  ParamsT<T> P;
+  double obstacle[6];
+  const double* path;      // [Tlen][2]
+  const double* orient;    // [Tlen]
+  const double* x0;        // [B][5]
+  double* traj;            // [B][Tlen][5]
+  double* ctrl;            // [B][Tlen][2]
+  int* status;             // [B][Tlen]
+  int* iters;              // [B][Tlen]
+  T* slab;
+  double desired_velocity;
+  double l_wb, dt;
+  int B, Tlen;
+};
+
+__device__ __forceinline__ void plant_euler(double* x, double u0, double u1, double dt, double l_wb) {
+  // shift_movement: st = x0 + delta_t * f(x0, u[:,0])   (optimizer.py:649-650; KS model configuration.py:364-368)
+  double s, c;
+  sincos(x[4], &s, &c);
+  const double v = x[3], tn = tan(x[2]);
+  x[0] += dt * v * c; x[1] += dt * v * s; x[2] += dt * u0; x[3] += dt * u1; x[4] += dt * v / l_wb * tn;
+}
+
+__device__ __forceinline__ void ref_window_rows(int i, int N, int Tlen, const double* path, const double* orient, double vdes,
+                                                const double* x_now, double* xref /* [N+1][5] */) {
+  // desired_command_and_trajectory (optimizer.py:657-702, quirk Q8)
+  for (int j = 0; j < 5; ++j) xref[j] = x_now[j];
+  for (int k = 0; k < N; ++k) {
+    const int idx = (i >= Tlen - N) ? (k + (Tlen - N)) : (i + k + 1);
+    double* r = xref + 5 * (k + 1);
+    r[0] = path[2 * idx]; r[1] = path[2 * idx + 1]; r[2] = 0.0; r[3] = vdes; r[4] = orient[idx];
+  }
+}
+
+template <typename T, int LANES, bool SMEM_WS>
+__global__ void __launch_bounds__(32, 1) mpc_closed_loop_kernel(const LoopArgs<T> a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int N = a.P.N;
+  const Layout L(N);
+  const int base = tile * LANES;
+  const int nvalid = min(LANES, a.B - base);
+  const bool valid = lane < nvalid;
+  const int b = base + (valid ? lane : 0);
+  T* slab_s = reinterpret_cast<T*>(smem_raw);
+  T* slab_g = a.slab ? a.slab + (size_t)tile * L.words * LANES : nullptr;
+  T* wsbase = SMEM_WS ? slab_s : slab_g;
+  double* stage = SMEM_WS ? reinterpret_cast<double*>(slab_s + (size_t)L.o_K * LANES) : reinterpret_cast<double*>(smem_raw);
+  const int nx = 5 * (N + 1), nu = 2 * N;
+  double* my_xref = stage + (size_t)(lane < LANES ? lane : 0) * nx;
+  double* my_X = stage + (size_t)LANES * nx + (size_t)(lane < LANES ? lane : 0) * nx;
+  double* my_U = stage + (size_t)2 * LANES * nx + (size_t)(lane < LANES ? lane : 0) * nu;
+
+  Ws<T, LANES> ws{wsbase + (lane < LANES ? lane : 0)};
+  T obs[6];
+  Solver<T, LANES> S(a.P, ws, obs);
+  ProbState<T> st;
+  double x[5];
+  if (valid) {
+    for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
+    // first parameter block and warm start: the initial state tiled, controls zero (optimizer.py:578-583, quirk Q4)
+    for (int k = 0; k <= N; ++k)
+      for (int j = 0; j < 5; ++j) { my_xref[5 * k + j] = x[j]; my_X[5 * k + j] = x[j]; }
+    for (int k = 0; k < nu; ++k) my_U[k] = 0.0;
+  }
+  for (int i = 0; i < a.Tlen; ++i) {
+    if (valid) {
+      if (a.traj) for (int j = 0; j < 5; ++j) a.traj[((size_t)b * a.Tlen + i) * 5 + j] = x[j];   // quirk Q12
+      S.load(my_xref, my_X, my_U, a.obstacle, obs);
+    }
+    __syncwarp();
+    if (valid) S.init(st); else { st.done = 1; }
+    for (int it = 0; it < a.P.max_iter; ++it) {
+      if (__all_sync(0xffffffffu, st.done)) break;
+      if (!st.done) S.iterate(st);
+    }
+    __syncwarp();
+    if (valid) {
+      // the solve clobbered the aliased staging: rebuild this step's window, then write the solution over it
+      if (i == 0) { for (int k = 0; k <= N; ++k) for (int j = 0; j < 5; ++j) my_xref[5 * k + j] = x[j]; }
+      else ref_window_rows(i - 1, N, a.Tlen, a.path, a.orient, a.desired_velocity, x, my_xref);
+      S.store(my_xref, my_X, my_U);
+      const double u0 = my_U[0], u1 = my_U[1];
+      if (a.ctrl) { a.ctrl[((size_t)b * a.Tlen + i) * 2] = u0; a.ctrl[((size_t)b * a.Tlen + i) * 2 + 1] = u1; }
+      if (a.status) a.status[(size_t)b * a.Tlen + i] = st.status;
+      if (a.iters) a.iters[(size_t)b * a.Tlen + i] = st.iters;
+      plant_euler(x, u0, u1, a.dt, a.l_wb);
+      // shift the warm start one stage, repeating the last (optimizer.py:652-653)
+      for (int k = 0; k < N - 1; ++k) { my_U[2 * k] = my_U[2 * k + 2]; my_U[2 * k + 1] = my_U[2 * k + 3]; }
+      for (int k = 0; k < N; ++k) for (int j = 0; j < 5; ++j) my_X[5 * k + j] = my_X[5 * (k + 1) + j];
+      // next window from the new state (optimizer.py:628)
+      ref_window_rows(i, N, a.Tlen, a.path, a.orient, a.desired_velocity, x, my_xref);
+    }
+    __syncwarp();
+  }
+}
+
+// ===================================================================================================== small kernels
+__global__ void plant_step_shift_kernel(double* x, double* U, double* X, double* u_applied, int B, int N, double dt, double l_wb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double* xb = x + (size_t)b * 5;
+  double* Ub = U + (size_t)b * 2 * N;
+  double* Xb = X + (size_t)b * 5 * (N + 1);
+  const double u0 = Ub[0], u1 = Ub[1];
+  if (u_applied) { u_applied[2 * b] = u0; u_applied[2 * b + 1] = u1; }
+  double xs[5];
+  for (int j = 0; j < 5; ++j) xs[j] = xb[j];
+  plant_euler(xs, u0, u1, dt, l_wb);
+  for (int j = 0; j < 5; ++j) xb[j] = xs[j];
+  for (int k = 0; k < N - 1; ++k) { Ub[2 * k] = Ub[2 * k + 2]; Ub[2 * k + 1] = Ub[2 * k + 3]; }
+  for (int k = 0; k < N; ++k) for (int j = 0; j < 5; ++j) Xb[5 * k + j] = Xb[5 * (k + 1) + j];
+}
+
+__global__ void build_ref_window_kernel(int i, int Tlen, const double* path, const double* orient, double vdes, const double* x,
+                                        double* xref, int B, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  ref_window_rows(i, N, Tlen, path, orient, vdes, x + (size_t)b * 5, xref + (size_t)b * 5 * (N + 1));
+}
+
+// ===================================================================================================== handle
+struct mpcb200_handle {
+  mpcb200_config cfg;
+  int lanes;            // problems per CTA
+  bool smem_ws;         // slab in shared memory
+  size_t smem_bytes;
+  int words;
+  void* slab;           // global slab image (stepwise mode or global-workspace mode)
+  void* state;
+  void* obs_shift;
+  size_t elem;          // sizeof(T)
+  int64_t launches;
+  // stepwise-mode context
+  const double* sw_xref;
+  int sw_B;
+  // host-path staging
+  double *d_xref, *d_X, *d_U;
+  int *d_status, *d_iters;
+  double *h_pin;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  if (h) h->err = buf; else g_create_err = buf;
+  return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
+
+template <typename T, int LANES, bool SMEM_WS>
+static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s) {
+  const int tiles = (a.B + LANES - 1) / LANES;
+  cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<T, LANES, SMEM_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) return e;
+  mpc_solve_kernel<T, LANES, SMEM_WS><<<tiles, 32, h->smem_bytes, s>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
+template <typename T, int LANES, bool SMEM_WS>
+static cudaError_t launch_loop(mpcb200_handle* h, const LoopArgs<T>& a, cudaStream_t s) {
+  const int tiles = (a.B + LANES - 1) / LANES;
+  cudaError_t e = cudaFuncSetAttribute(mpc_closed_loop_kernel<T, LANES, SMEM_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) return e;
+  mpc_closed_loop_kernel<T, LANES, SMEM_WS><<<tiles, 32, h->smem_bytes, s>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s) {
+  if (h->smem_ws) {
+    if (h->lanes == 32) return launch_solve<T, 32, true>(h, a, s);
+    if (h->lanes == 16) return launch_solve<T, 16, true>(h, a, s);
+    return launch_solve<T, 8, true>(h, a, s);
+  }
+  return launch_solve<T, 32, false>(h, a, s);
+}
+template <typename T>
+static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t s) {
+  if (h->smem_ws) {
+    if (h->lanes == 32) return launch_loop<T, 32, true>(h, a, s);
+    if (h->lanes == 16) return launch_loop<T, 16, true>(h, a, s);
+    return launch_loop<T, 8, true>(h, a, s);
+  }
+  return launch_loop<T, 32, false>(h, a, s);
+}
+
+template <typename T>
+static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref, double* X, double* U, int* status, int* iters,
+                    int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  SolveArgs<T> a;
+  a.P = params_from_config<T>(h->cfg);
+  for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
+  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
+  a.slab = (T*)h->slab; a.state = (ProbState<T>*)h->state; a.obs_shift = (T*)h->obs_shift;
+  a.B = B; a.mode = mode; a.n_iter = n_iter;
+  cudaError_t e = dispatch_solve<T>(h, a, s);
+  if (e != cudaSuccess) return fail(h, "mpc_solve_kernel launch", e);
+  return 0;
+}
+
+extern "C" {
+
+int32_t mpcb200_abi_version(void) { return MPCB200_ABI_VERSION; }
+
+void mpcb200_default_config(mpcb200_config* cfg, int32_t N, int32_t precision) { default_config(cfg, N, precision); }
+
+const char* mpcb200_last_error(const mpcb200_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
+  mpcb200_handle* h = nullptr;
+  if (!cfg || !out) { g_create_err = "null argument"; return -2; }
+  if (cfg->abi_version != MPCB200_ABI_VERSION) { g_create_err = "abi_version mismatch"; return -2; }
+  if (cfg->N < 4 || cfg->N > 512 || cfg->max_batch < 1) { g_create_err = "N must be in [4, 512], max_batch >= 1"; return -2; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { fail(nullptr, "no CUDA device (libmpcb200 has no CPU path)", e); return -3; }
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 9) { g_create_err = "libmpcb200 needs TMA bulk copies (sm_90+); built for sm_100a"; return -3; }
+  h = new (std::nothrow) mpcb200_handle();
+  if (!h) { g_create_err = "out of host memory"; return -4; }
+  h->cfg = *cfg;
+  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr;
+  h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
+  h->sw_xref = nullptr; h->sw_B = 0;
+  const Layout L(cfg->N);
+  h->words = L.words;
+  h->elem = cfg->precision == MPCB200_F64 ? 8 : 4;
+  const size_t smem_max = prop.sharedMemPerBlockOptin;   // 227 KB on B200
+  const size_t reserve = 1024;
+  h->smem_ws = false; h->lanes = 32;
+  for (int lanes : {32, 16, 8}) {
+    const size_t need = (size_t)L.words * lanes * h->elem;
+    if (need + reserve <= smem_max) { h->smem_ws = true; h->lanes = lanes; h->smem_bytes = need; break; }
+  }
+  if (!h->smem_ws) {
+    h->lanes = 32;
+    h->smem_bytes = (size_t)32 * (12 * cfg->N + 10) * sizeof(double);   // float64 staging only
+    if (h->smem_bytes + reserve > smem_max) { g_create_err = "horizon too long for the staging buffer"; delete h; return -2; }
+  }
+  const size_t tiles = ((size_t)cfg->max_batch + h->lanes - 1) / h->lanes;
+  if (cudaMalloc(&h->slab, tiles * L.words * h->lanes * h->elem) != cudaSuccess ||
+      cudaMalloc(&h->state, (size_t)cfg->max_batch * sizeof(ProbState<double>)) != cudaSuccess ||
+      cudaMalloc(&h->obs_shift, (size_t)cfg->max_batch * 6 * h->elem) != cudaSuccess) {
+    fail(nullptr, "cudaMalloc of solver scratch", cudaGetLastError());
+    mpcb200_destroy(h);
+    return -4;
+  }
+  *out = h;
+  return 0;
+}
+
+void mpcb200_destroy(mpcb200_handle* h) {
+  if (!h) return;
+  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift);
+  cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  delete h;
+}
+
+int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters,
+                  int32_t B, void* stream) {
+  if (!h) return -2;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
+  return do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
+}
+
+int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X, const double* d_U, int32_t B, void* stream) {
+  if (!h) return -2;
+  h->sw_xref = d_xref; h->sw_B = B;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_BEGIN, 0, d_xref, (double*)d_X, (double*)d_U, nullptr, nullptr, B, s);
+  return do_solve<float>(h, MODE_BEGIN, 0, d_xref, (double*)d_X, (double*)d_U, nullptr, nullptr, B, s);
+}
+
+int mpcb200_sqp_iter(mpcb200_handle* h, int32_t n_iter, void* stream) {
+  if (!h || !h->sw_xref) { if (h) h->err = "sqp_iter without sqp_begin"; return -2; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ITER, n_iter, h->sw_xref, nullptr, nullptr, nullptr, nullptr, h->sw_B, s);
+  return do_solve<float>(h, MODE_ITER, n_iter, h->sw_xref, nullptr, nullptr, nullptr, nullptr, h->sw_B, s);
+}
+
+int mpcb200_sqp_end(mpcb200_handle* h, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters, void* stream) {
+  if (!h || !h->sw_xref) { if (h) h->err = "sqp_end without sqp_begin"; return -2; }
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (h->cfg.precision == MPCB200_F64) rc = do_solve<double>(h, MODE_END, 0, h->sw_xref, d_X, d_U, d_status, d_iters, h->sw_B, s);
+  else rc = do_solve<float>(h, MODE_END, 0, h->sw_xref, d_X, d_U, d_status, d_iters, h->sw_B, s);
+  h->sw_xref = nullptr;
+  return rc;
+}
+
+int mpcb200_plant_step_shift(mpcb200_handle* h, double* d_x, double* d_U, double* d_X, double* d_u_applied, int32_t B, void* stream) {
+  if (!h) return -2;
+  if (B <= 0) return 0;
+  plant_step_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_x, d_U, d_X, d_u_applied, B, h->cfg.N, h->cfg.dt, h->cfg.l_wb);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, "plant_step_shift launch", e);
+  return 0;
+}
+
+int mpcb200_build_ref_window(mpcb200_handle* h, int32_t i, int32_t iter_length, const double* d_path, const double* d_orientation,
+                             double desired_velocity, const double* d_x, double* d_xref, int32_t B, void* stream) {
+  if (!h) return -2;
+  if (B <= 0) return 0;
+  if (h->cfg.N > iter_length) { h->err = "predict_horizon exceeds iter_length"; return -2; }
+  build_ref_window_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(i, iter_length, d_path, d_orientation, desired_velocity, d_x,
+                                                                             d_xref, B, h->cfg.N);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, "build_ref_window launch", e);
+  return 0;
+}
+
+int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_path, const double* d_orientation, double desired_velocity,
+                        const double* d_x0, double* d_traj, double* d_ctrl, int32_t* d_status, int32_t* d_iters, int32_t B, void* stream) {
+  if (!h) return -2;
+  if (B <= 0) return 0;
+  if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  if (h->cfg.N > iter_length) { h->err = "predict_horizon exceeds iter_length"; return -2; }
+  cudaError_t e;
+  if (h->cfg.precision == MPCB200_F64) {
+    LoopArgs<double> a;
+    a.P = params_from_config<double>(h->cfg);
+    for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
+    a.path = d_path; a.orient = d_orientation; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
+    a.slab = (double*)h->slab; a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
+    e = dispatch_loop<double>(h, a, (cudaStream_t)stream);
+  } else {
+    LoopArgs<float> a;
+    a.P = params_from_config<float>(h->cfg);
+    for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
+    a.path = d_path; a.orient = d_orientation; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
+    a.slab = (float*)h->slab; a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
+    e = dispatch_loop<float>(h, a, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return fail(h, "mpc_closed_loop_kernel launch", e);
+  return 0;
+}
+
+int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, double* h_U, int32_t* h_status, int32_t* h_iters, int32_t B) {
+  if (!h) return -2;
+  if (B <= 0) return 0;
+  if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  const int N = h->cfg.N;
+  const size_t nx = (size_t)5 * (N + 1), nu = (size_t)2 * N, mb = h->cfg.max_batch;
+  if (!h->d_xref) {
+    CK(cudaMalloc(&h->d_xref, mb * nx * 8)); CK(cudaMalloc(&h->d_X, mb * nx * 8)); CK(cudaMalloc(&h->d_U, mb * nu * 8));
+    CK(cudaMalloc(&h->d_status, mb * 4)); CK(cudaMalloc(&h->d_iters, mb * 4));
+  }
+  cudaStream_t s = 0;
+  CK(cudaMemcpyAsync(h->d_xref, h_xref, B * nx * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_X, h_X, B * nx * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_U, h_U, B * nu * 8, cudaMemcpyHostToDevice, s));
+  int rc = mpcb200_solve(h, h->d_xref, h->d_X, h->d_U, h->d_status, h->d_iters, B, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_X, h->d_X, B * nx * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_U, h->d_U, B * nu * 8, cudaMemcpyDeviceToHost, s));
+  if (h_status) CK(cudaMemcpyAsync(h_status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (h_iters) CK(cudaMemcpyAsync(h_iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int64_t mpcb200_launch_count(const mpcb200_handle* h) { return h ? h->launches : 0; }
+int32_t mpcb200_workspace_words(const mpcb200_handle* h) { return h ? h->words : 0; }
+int32_t mpcb200_slab_in_smem(const mpcb200_handle* h) { return h ? (h->smem_ws ? h->lanes : 0) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+"""B200Optimizer -- drop-in for `CasadiOptimizer` behind the reference's `Optimizer` base class.
+
+Reference interface mirrored (paths relative to /root/reference/):
+    Optimizer.__init__(configuration, init_values, predict_horizon)      MPC_Planner/optimizer.py:34-68
+    CasadiOptimizer.optimize() -> (states[T,5], controls[T,2], t[T])      MPC_Planner/optimizer.py:562-643
+    call sites                                                             MPC_Planner/mpc_planner.py:302, 309
+
+When `MPC_Planner.optimizer` is importable (casadi, forcespro, commonroad ... installed) `B200Optimizer` subclasses the
+real `Optimizer`; otherwise it subclasses `OptimizerBase`, an attribute-compatible mirror.  Either way the numerical
+work is done by libmpcb200.so (hand-written sm_100a CUDA) through ctypes; torch is used only for device buffers and
+streams.  There is no CPU path: without CUDA + the built library this module raises.
+
+Additive batched API (new): `solve_batch`, `optimize_batch`.
+"""
+import time
+
+import numpy as np
+
+from . import _capi
+from .scenarios import reference_window
+
+L_WB = 2.5789128      # parameters_vehicle2: p.a + p.b (configuration.py:362-363)
+L_FRICTION = 2.578    # literal in the friction row (optimizer.py:378)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# geometry helpers restated for floats (configuration.py:40-93); the reference's versions call ca.cos/ca.sin
+def compute_approximating_circle_radius(length, width):
+    """configuration.py:40-66"""
+    assert length >= 0 and width >= 0, 'Invalid vehicle dimensions = {}'.format([length, width])
+    if np.isclose(length, 0.0) and np.isclose(width, 0.0):
+        return 0.0, 0.0
+    square_length = length / 3
+    diagonal_square = np.sqrt((square_length / 2) ** 2 + (width / 2) ** 2)
+    if diagonal_square > round(diagonal_square, 1):
+        approx_radius = round(diagonal_square, 1) + 0.1
+    else:
+        approx_radius = round(diagonal_square, 1)
+    return approx_radius, round(square_length * 2, 1)
+
+
+def compute_centers_of_approximation_circles(x_position, y_position, v_length, v_width, orientation):
+    """configuration.py:69-93"""
+    _, disc_distance = compute_approximating_circle_radius(v_length, v_width)
+    distance_centers = disc_distance / 2
+    c, s = float(np.cos(orientation)), float(np.sin(orientation))
+    center = [x_position, y_position]
+    center_fw = [x_position + (distance_centers / 2) * c, y_position + (distance_centers / 2) * s]
+    center_rw = [x_position - (distance_centers / 2) * c, y_position - (distance_centers / 2) * s]
+    return center, center_fw, center_rw
+
+
+class _Steering:
+    min, max, v_min, v_max = -1.066, 1.066, -0.4, 0.4
+
+
+class _Longitudinal:
+    v_max, a_max = 50.8, 11.5
+
+
+class VehicleParameters2:
+    """The fields of vehiclemodels.parameters_vehicle2 (BMW 320i) the optimizer reads (optimizer.py:37-46, 68)."""
+    steering = _Steering
+    longitudinal = _Longitudinal
+    l, w = 4.508, 1.610
+    a, b = 1.1561957, 1.4227171   # a + b = 2.5789128
+
+
+def obstacle_circles_and_radius(static_obstacle, p=VehicleParameters2):
+    """Optimizer.__init__ lines 60-68: obstacle circle centres, r_ego + r_obs, ego circle offset."""
+    circles = compute_centers_of_approximation_circles(static_obstacle["position_x"], static_obstacle["position_y"],
+                                                       static_obstacle["length"], static_obstacle["width"],
+                                                       static_obstacle["orientation"])
+    r_obs, _ = compute_approximating_circle_radius(static_obstacle["length"], static_obstacle["width"])
+    r_ego, dd = compute_approximating_circle_radius(p.l, p.w)
+    return circles, r_ego + r_obs, dd / 4.0
+
+
+class OptimizerBase(object):
+    """Attribute-compatible mirror of `Optimizer` (optimizer.py:33-83) for environments without casadi et al."""
+
+    def __init__(self, configuration, init_values, predict_horizon):
+        self.configuration = configuration
+        self.delta_min = configuration.p.steering.min
+        self.delta_max = configuration.p.steering.max
+        self.deltav_min = configuration.p.steering.v_min
+        self.deltav_max = configuration.p.steering.v_max
+        self.v_min = 0
+        self.v_max = configuration.p.longitudinal.v_max
+        self.a_max = configuration.p.longitudinal.a_max
+        self.init_position, self.init_velocity, self.init_acceleration, self.init_orientation = \
+            init_values[0], init_values[1], init_values[2], init_values[3]
+        self.iter_length = configuration.iter_length
+        self.delta_t = configuration.delta_t
+        self.desired_velocity = configuration.desired_velocity
+        self.resampled_path_points = configuration.reference_path
+        self.orientation = configuration.orientation
+        self.predict_horizon = predict_horizon
+        self.weights_setting = configuration.weights_setting
+        so = configuration.static_obstacle
+        self.obstacle_circles_centers_tuple = compute_centers_of_approximation_circles(
+            so["position_x"], so["position_y"], so["length"], so["width"], so["orientation"])
+        self.radius_obstacle, _ = compute_approximating_circle_radius(so["length"], so["width"])
+        self.radius_ego, _ = compute_approximating_circle_radius(configuration.p.l, configuration.p.w)
+
+    def equal_constraints(self, *args, **kwargs):
+        pass
+
+    def inequal_constraints(self, *args, **kwargs):
+        pass
+
+    def cost_function(self, *args, **kwargs):
+        pass
+
+    def solver(self):
+        pass
+
+    def optimize(self):
+        pass
+
+
+try:  # the real base class when the reference and its dependencies are importable
+    from MPC_Planner.optimizer import Optimizer as _RefOptimizer  # type: ignore
+    _Base = _RefOptimizer
+except Exception:  # casadi / forcespro / commonroad absent (this image)
+    _Base = OptimizerBase
+
+
+def _require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise _capi.Mpcb200Error("B200Optimizer needs a CUDA device; there is no CPU fallback")
+    return torch
+
+
+class B200Optimizer(_Base):
+    """Batched nonlinear-MPC optimizer on one B200.  `optimize()` keeps the reference's contract (B = 1)."""
+
+    def __init__(self, configuration, init_values, predict_horizon, precision="f32", hessian="exact",
+                 max_batch=4096, device=None, max_iter=100, **solver_opts):
+        super(B200Optimizer, self).__init__(configuration, init_values, predict_horizon)
+        torch = _require_cuda()
+        self.torch = torch
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        N = int(predict_horizon)
+        cfg = _capi.default_config(N, _capi.F64 if precision in ("f64", "float64", 1) else _capi.F32)
+        cfg.device = self.device_index
+        cfg.max_batch = int(max_batch)
+        cfg.hessian = _capi.HESS_EXACT if hessian in ("exact", 1) else _capi.HESS_GAUSS_NEWTON
+        cfg.max_iter = int(max_iter)
+        cfg.dt = float(self.delta_t)
+        cfg.l_wb = float(getattr(configuration.p, "a", VehicleParameters2.a) + getattr(configuration.p, "b", VehicleParameters2.b))
+        cfg.l_fric = L_FRICTION
+        w = self.weights_setting
+        for i, k in enumerate(("weight_x", "weight_y", "weight_steering_angle", "weight_velocity", "weight_heading_angle")):
+            cfg.Q[i] = float(w[k])
+        cfg.R[0] = float(w["weight_velocity_steering_angle"])
+        cfg.R[1] = float(w["weight_long_acceleration"])
+        cfg.deltav_min, cfg.deltav_max = float(self.deltav_min), float(self.deltav_max)
+        cfg.a_max = float(self.a_max)
+        cfg.delta_min, cfg.delta_max = float(self.delta_min), float(self.delta_max)
+        cfg.v_min, cfg.v_max = float(self.v_min), float(self.v_max)
+        cfg.r_sum = float(self.radius_ego + self.radius_obstacle)
+        _, dd = compute_approximating_circle_radius(configuration.p.l, configuration.p.w)
+        cfg.ego_offset = dd / 4.0
+        for j in range(3):
+            cfg.obstacle[2 * j] = float(self.obstacle_circles_centers_tuple[j][0])
+            cfg.obstacle[2 * j + 1] = float(self.obstacle_circles_centers_tuple[j][1])
+        for k, v in solver_opts.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.N = N
+        with torch.cuda.device(self.device):
+            self.handle = _capi.Handle(cfg)
+        self._path_d = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev(self, a):
+        t = self.torch
+        if isinstance(a, t.Tensor):
+            return a.to(device=self.device, dtype=t.float64).contiguous()
+        return t.as_tensor(np.ascontiguousarray(a, np.float64), device=self.device)
+
+    def _path_tensors(self):
+        if self._path_d is None:
+            self._path_d = (self._dev(np.asarray(self.resampled_path_points, float)[:, :2]),
+                            self._dev(np.asarray(self.orientation, float)))
+        return self._path_d
+
+    # ------------------------------------------------------------------ batched API (device tensors in / out)
+    def solve_batch(self, xref, X_init=None, U_init=None):
+        """One NLP solve per row (replaces optimizer.py:605-607).  xref [B,N+1,5] (row 0 = current state).
+        Returns (U*[B,N,2], X*[B,N+1,5], status[B] int32, iters[B] int32) as CUDA tensors (float64)."""
+        t = self.torch
+        xref = self._dev(xref)
+        B = xref.shape[0]
+        assert xref.shape[1:] == (self.N + 1, 5), xref.shape
+        X = (xref[:, :1, :].expand(B, self.N + 1, 5).contiguous() if X_init is None else self._dev(X_init).clone())
+        U = (t.zeros(B, self.N, 2, dtype=t.float64, device=self.device) if U_init is None else self._dev(U_init).clone())
+        status = t.empty(B, dtype=t.int32, device=self.device)
+        iters = t.empty(B, dtype=t.int32, device=self.device)
+        h = self.handle
+        h.check(h.lib.mpcb200_solve(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(),
+                                    iters.data_ptr(), B, self._stream()))
+        return U, X, status, iters
+
+    def solve_batch_stepwise(self, xref, X_init=None, U_init=None, n_iter=None):
+        """Same solve with one kernel launch per SQP iteration (KKT slab staged HBM<->smem by TMA each launch)."""
+        t = self.torch
+        xref = self._dev(xref)
+        B = xref.shape[0]
+        X = (xref[:, :1, :].expand(B, self.N + 1, 5).contiguous() if X_init is None else self._dev(X_init).clone())
+        U = (t.zeros(B, self.N, 2, dtype=t.float64, device=self.device) if U_init is None else self._dev(U_init).clone())
+        status = t.empty(B, dtype=t.int32, device=self.device)
+        iters = t.empty(B, dtype=t.int32, device=self.device)
+        h = self.handle
+        s = self._stream()
+        h.check(h.lib.mpcb200_sqp_begin(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), B, s))
+        for _ in range(self.cfg.max_iter if n_iter is None else n_iter):
+            h.check(h.lib.mpcb200_sqp_iter(h.h, 1, s))
+        h.check(h.lib.mpcb200_sqp_end(h.h, X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), s))
+        return U, X, status, iters
+
+    def solve_batch_host(self, xref, X_init, U_init):
+        """End-to-end call with HOST numpy buffers (H2D + solve + D2H inside the library, synchronous)."""
+        xref = np.ascontiguousarray(xref, np.float64)
+        X = np.ascontiguousarray(X_init, np.float64).copy()
+        U = np.ascontiguousarray(U_init, np.float64).copy()
+        B = xref.shape[0]
+        status = np.empty(B, np.int32)
+        iters = np.empty(B, np.int32)
+        h = self.handle
+        h.check(h.lib.mpcb200_solve_host(h.h, xref.ctypes.data, X.ctypes.data, U.ctypes.data, status.ctypes.data,
+                                         iters.ctypes.data, B))
+        return U, X, status, iters
+
+    def plant_step_shift(self, x, U, X):
+        """shift_movement (optimizer.py:645-655) on the device, in place.  Returns applied controls [B,2]."""
+        t = self.torch
+        B = x.shape[0]
+        u_applied = t.empty(B, 2, dtype=t.float64, device=self.device)
+        h = self.handle
+        h.check(h.lib.mpcb200_plant_step_shift(h.h, x.data_ptr(), U.data_ptr(), X.data_ptr(), u_applied.data_ptr(), B,
+                                               self._stream()))
+        return u_applied
+
+    def build_ref_window(self, i, x):
+        """desired_command_and_trajectory (optimizer.py:657-702) on the device -> X_ref [B,N+1,5]."""
+        t = self.torch
+        path, orient = self._path_tensors()
+        B = x.shape[0]
+        xref = t.empty(B, self.N + 1, 5, dtype=t.float64, device=self.device)
+        h = self.handle
+        h.check(h.lib.mpcb200_build_ref_window(h.h, int(i), int(self.iter_length), path.data_ptr(), orient.data_ptr(),
+                                               float(self.desired_velocity), x.data_ptr(), xref.data_ptr(), B,
+                                               self._stream()))
+        return xref
+
+    def optimize_batch(self, x0, return_device=False):
+        """The reference's whole receding-horizon loop (optimizer.py:596-631) for B egos, entirely on the device.
+        x0 [B,5] -> (states[B,T,5], controls[B,T,2], status[B,T], iters[B,T])."""
+        t = self.torch
+        x0 = self._dev(x0)
+        B, T = x0.shape[0], int(self.iter_length)
+        path, orient = self._path_tensors()
+        traj = t.empty(B, T, 5, dtype=t.float64, device=self.device)
+        ctrl = t.empty(B, T, 2, dtype=t.float64, device=self.device)
+        status = t.empty(B, T, dtype=t.int32, device=self.device)
+        iters = t.empty(B, T, dtype=t.int32, device=self.device)
+        h = self.handle
+        h.check(h.lib.mpcb200_closed_loop(h.h, T, path.data_ptr(), orient.data_ptr(), float(self.desired_velocity),
+                                          x0.data_ptr(), traj.data_ptr(), ctrl.data_ptr(), status.data_ptr(),
+                                          iters.data_ptr(), B, self._stream()))
+        if return_device:
+            return traj, ctrl, status, iters
+        return traj.cpu().numpy(), ctrl.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
+
+    # ------------------------------------------------------------------ the reference contract
+    def optimize(self):
+        """CasadiOptimizer.optimize() (optimizer.py:562-643): returns (traj_s[T,5], u[T,2], t_v[T]).
+
+        The loop shape is the reference's (solve -> first control -> plant step + shift -> next window); solve time per
+        step is measured like the reference does (wall clock around the solve, optimizer.py:603-608).  `noised` is
+        honoured with the reference's own noise law when N == 10 (optimizer.py:611-615, quirk Q9)."""
+        t = self.torch
+        N, T = self.N, int(self.iter_length)
+        init_state = np.array([self.init_position[0], self.init_position[1], 0.0, self.init_velocity,
+                               self.init_orientation], float)
+        x = self._dev(init_state[None, :])
+        xref = x[:, None, :].expand(1, N + 1, 5).contiguous()      # Q4: first parameter block = x0 tiled
+        X = xref.clone()
+        U = t.zeros(1, N, 2, dtype=t.float64, device=self.device)
+        traj, u_c, t_v = [], [], []
+        noised = bool(getattr(self.configuration, "noised", False))
+        for i in range(T):
+            t.cuda.synchronize(self.device)
+            t_ = time.time()
+            U, X, status, iters = self.solve_batch(xref, X, U)
+            t.cuda.synchronize(self.device)
+            t_v.append(time.time() - t_)
+            if noised:
+                if N != 10:
+                    raise ValueError("noised=True draws 20 = 2*10 samples in the reference (optimizer.py:613); N must be 10")
+                sigma = 0.1 if getattr(self.configuration, "use_case", "lane_following") == "lane_following" else 0.05
+                noise = np.random.normal(0, sigma, 20).reshape(2, N).T
+                U = U + self._dev(noise[None])
+            u_applied = self.plant_step_shift(x, U, X)
+            u_c.append(u_applied[0].cpu().numpy())
+            traj.append(x[0].cpu().numpy().copy())
+            xref = self.build_ref_window(i, x)
+        traj_s = np.array(traj)
+        traj_s = np.insert(traj_s, 0, init_state, axis=0)
+        traj_s = np.delete(traj_s, -1, axis=0)
+        return traj_s, np.array(u_c), np.array(t_v)
+
+
+def make_configuration(scenario, predict_horizon=None, framework_name="casadi", noised=False):
+    """A `PlanningConfiguration`-shaped object (configuration.py:106-336) built from mpc_b200.scenarios data, for use
+    where commonroad is not installed.  Only the fields Optimizer reads are populated."""
+    from types import SimpleNamespace
+    return SimpleNamespace(p=VehicleParameters2, iter_length=scenario.iter_length, delta_t=scenario.dt,
+                           desired_velocity=scenario.desired_velocity, reference_path=scenario.reference_path,
+                           orientation=scenario.orientation, weights_setting=scenario.weights_setting,
+                           static_obstacle=scenario.static_obstacle, noised=noised, use_case=scenario.use_case,
+                           wheelbase=scenario.wheelbase, framework_name=framework_name,
+                           predict_horizon=predict_horizon)
+
+
+def init_values_from_state(x0):
+    """(position, velocity, acceleration, orientation) as MPCPlanner.get_init_values returns (mpc_planner.py:30-59)."""
+    return (np.array([x0[0], x0[1]]), float(x0[3]), 0.0, float(x0[4]))

@@ -1,0 +1,54 @@
+"""TEST TOOLING ONLY: ctypes loader for the g++ build of the device solver core (tests/host_sim/host_sim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Config(C.Structure):
+    """Mirror of mpcb200_config (include/mpcb200.h)."""
+    _fields_ = ([(n, C.c_int32) for n in ("abi_version", "device", "N", "max_batch", "precision", "hessian",
+                                          "max_iter", "ls_max")] +
+                [("dt", C.c_double), ("l_wb", C.c_double), ("l_fric", C.c_double), ("Q", C.c_double * 5),
+                 ("R", C.c_double * 2), ("deltav_min", C.c_double), ("deltav_max", C.c_double), ("a_max", C.c_double),
+                 ("delta_min", C.c_double), ("delta_max", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double),
+                 ("r_sum", C.c_double), ("ego_offset", C.c_double), ("obstacle", C.c_double * 6),
+                 ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_factor", C.c_double), ("tol_step", C.c_double),
+                 ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double)])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(HERE, "libhostsim.so")
+        src = os.path.join(HERE, "host_sim.cpp")
+        core = os.path.join(HERE, "..", "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc", "sqp_core.cuh")
+        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], cwd=HERE)
+        _lib = C.CDLL(so)
+    return _lib
+
+
+def default_config(N, precision=0):
+    c = Config()
+    lib().hostsim_default_config(C.byref(c), N, precision)
+    return c
+
+
+def solve(cfg, xref, X, U, trace=0):
+    xref = np.ascontiguousarray(xref, np.float64)
+    X = np.ascontiguousarray(X, np.float64).copy()
+    U = np.ascontiguousarray(U, np.float64).copy()
+    B = xref.shape[0]
+    st = np.zeros(B, np.int32)
+    it = np.zeros(B, np.int32)
+    kkt = np.zeros(B, np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hostsim_solve(C.byref(cfg), p(xref), p(X), p(U), p(st), p(it), p(kkt), B, trace)
+    return X, U, st, it, kkt

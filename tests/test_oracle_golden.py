@@ -1,0 +1,169 @@
+"""Pins the oracle (oracle/nlp.py, oracle/ipm.py) against everything the reference holds for this path:
+recorded plant transitions, the CasADi-generated C model, the exact step-0 optimum, and an independent SLSQP solve."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ipm, nlp
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_euler_transitions_recorded_casadi_runs_exact():
+    d = np.load(os.path.join(G, "plant_transitions.npz"))
+    xn = nlp.euler_step(d["casadi_x"], d["casadi_u"], 0.1)
+    assert np.abs(xn - d["casadi_xnext"]).max() <= 1e-12     # 127 transitions, l = 2.5789128
+
+
+def test_rk4_transitions_recorded_forcespro_runs_exact():
+    d = np.load(os.path.join(G, "plant_transitions.npz"))
+    xn = nlp.rk4_step(d["forcespro_x"], d["forcespro_u"], 0.1)
+    assert np.abs(xn - d["forcespro_xnext"]).max() <= 1e-12
+
+
+def test_recorded_initial_states():
+    d = np.load(os.path.join(G, "plant_transitions.npz"))
+    assert np.allclose(d["casadi_x"][0], [29.9948, -1.1501, 0.0, 20.0, 0.03495])
+    assert np.allclose(d["casadi_x"][58], [0.0, 0.0, 0.0, 6.8062, -0.4268])
+
+
+def test_forces_model_dynamics_and_jacobian():
+    k = np.load(os.path.join(G, "forces_model_kat.npz"))
+    z = k["z"]
+    x, u = z[:, 2:7], z[:, 0:2]
+    assert np.abs(nlp.rk4_step(x, u, 0.1) - k["dynamics"]).max() <= 1e-12
+    # Jacobian of the RK4 step wrt z = [u; x] by central differences of the restated f
+    eps = 1e-6
+    for i in range(8):
+        J = np.zeros((5, 7))
+        for j in range(7):
+            zp, zm = z[i].copy(), z[i].copy()
+            zp[j] += eps
+            zm[j] -= eps
+            J[:, j] = (nlp.rk4_step(zp[2:], zp[:2], 0.1) - nlp.rk4_step(zm[2:], zm[:2], 0.1)) / (2 * eps)
+        assert np.abs(J - k["ddynamics"][i]).max() <= 1e-6
+
+
+def test_forces_model_friction_literal_and_circle_geometry():
+    k = np.load(os.path.join(G, "forces_model_kat.npz"))
+    z, p, h = k["z"], k["p"], k["inequalities"]
+    a, de, v, psi = z[:, 1], z[:, 4], z[:, 5], z[:, 6]
+    # friction term of the Forcespro formulation uses the same 2.578 literal as optimizer.py:378
+    assert np.allclose(h[:, 0], a ** 2 + (v * (v * np.tan(de) / nlp.L_FRICTION)) ** 2, rtol=1e-13)
+    # ego circle centres: compute_centers_of_approximation_circles with (4.508, 1.610) -> offset 0.75
+    for i in range(len(z)):
+        c, f, r = nlp.compute_centers_of_approximation_circles(z[i, 2], z[i, 3], 4.508, 1.610, psi[i])
+        obst = p[i, 4:10].reshape(3, 2)
+        d2 = [[(e[0] - o[0]) ** 2 + (e[1] - o[1]) ** 2 for o in obst] for e in (c, f, r)]
+        assert np.allclose(h[i, 1:], np.array(d2).reshape(-1), rtol=1e-12)
+
+
+def test_circle_radii_constants():
+    assert nlp.compute_approximating_circle_radius(4.508, 1.610) == (pytest.approx(1.2), pytest.approx(3.0))
+    assert nlp.compute_approximating_circle_radius(6.0, 3.5) == (pytest.approx(2.1), pytest.approx(4.0))
+    assert nlp.compute_approximating_circle_radius(0.0, 0.0) == (0.0, 0.0)
+
+
+def _zam(weights="LF", N=10):
+    import mpc_b200
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF" if weights == "LF" else "ZAM_Over-1_1_CA")
+    xref = np.tile(sc.x0, (N + 1, 1))
+    return sc, nlp.make_nlp(N, sc.dt, sc.weights_setting, xref, sc.static_obstacle), xref
+
+
+@pytest.mark.parametrize("weights", ["LF", "CA"])
+def test_step0_known_answer_friction_row_active(weights):
+    """Q3/Q4/Q7: first MPC step regulates to x0, wants to brake harder than allowed, is stopped at a0 = -sqrt(11.5)."""
+    sc, d, xref = _zam(weights)
+    r = ipm.solve(d, nlp.pack(np.zeros((10, 2)), xref))
+    U, X = nlp.split(r["w"], 10)
+    assert r["status"] == 1 and r["kkt"] < 1e-8
+    assert abs(U[0, 1] + np.sqrt(11.5)) < 1e-8
+    assert abs(U[0, 0]) < 1e-5
+    if weights == "LF":   # profile found independently with SLSQP in the survey session (3 digits)
+        assert np.allclose(U[:, 1], [-3.391, -30.63, -23.29, -16.72, -11.04, -6.38, -2.83, -0.51, 0.47, 0.0], atol=6e-3)
+        assert np.allclose(X[:, 3], [20, 19.661, 16.598, 14.269, 12.598, 11.494, 10.856, 10.573, 10.522, 10.569, 10.569], atol=2e-3)
+
+
+def test_verbatim_abs_friction_row_matches_smooth_statement_away_from_kink():
+    sc, d, xref = _zam("LF")
+    r1 = ipm.solve(d, nlp.pack(np.zeros((10, 2)), xref))
+    d.friction_smooth = False
+    r2 = ipm.solve(d, nlp.pack(np.zeros((10, 2)), xref))
+    assert r2["status"] == 1 and np.abs(r1["w"] - r2["w"]).max() < 1e-7
+
+
+def test_oracle_vs_scipy_slsqp_small():
+    """Independent solver on the same NLP (single shooting over U, N=6)."""
+    from scipy.optimize import minimize
+    import mpc_b200
+    N = 6
+    sc, x0, xref, X, U = mpc_b200.make_batch("ZAM_Over-1_1_LF", 2, N, 7)
+    d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[0], sc.static_obstacle)
+    r = ipm.solve(d, nlp.pack(U[0], X[0]))
+    assert r["status"] == 1
+
+    def rollout(u):
+        u = u.reshape(N, 2)
+        xs = [xref[0, 0]]
+        for k in range(N):
+            xs.append(nlp.euler_step(xs[-1], u[k], sc.dt))
+        return np.array(xs)
+
+    def f(u):
+        return nlp.cost(d, nlp.pack(u.reshape(N, 2), rollout(u)))
+
+    lbg, ubg, lbx, ubx = nlp.g_bounds(d)
+
+    def ineq(u):
+        xs = rollout(u)
+        w = nlp.pack(u.reshape(N, 2), xs)
+        g = nlp.g_fun(d, w)
+        out = [ubg[0] - g[0], g[0] - lbg[0]]
+        out += list(g[1 + 5 * (N + 1):] - d.r_sum)
+        out += list(xs[:, 2] - d.veh.delta_min) + list(d.veh.delta_max - xs[:, 2]) + list(xs[:, 3]) + list(d.veh.v_max - xs[:, 3])
+        return np.array(out)
+
+    bnds = [(d.veh.deltav_min, d.veh.deltav_max), (None, d.veh.a_max)] * N
+    s = minimize(f, np.zeros(2 * N), method="SLSQP", bounds=bnds, constraints=[{"type": "ineq", "fun": ineq}],
+                 options={"ftol": 1e-14, "maxiter": 500})
+    Uo, _ = nlp.split(r["w"], N)
+    assert np.abs(s.x.reshape(N, 2) - Uo).max() < 2e-4
+    assert abs(s.fun - r["obj"]) < 1e-6 * max(1.0, abs(r["obj"]))
+
+
+def test_kkt_checker_rejects_perturbed_point():
+    sc, d, xref = _zam("LF")
+    r = ipm.solve(d, nlp.pack(np.zeros((10, 2)), xref))
+    assert ipm.kkt_error(d, r["w"])[0] < 1e-8
+    w = r["w"].copy()
+    w[3] += 1e-3
+    assert ipm.kkt_error(d, w)[0] > 1e-5
+
+
+def test_golden_nlp_solutions_reproduce():
+    g = np.load(os.path.join(G, "nlp_solutions.npz"))
+    import mpc_b200
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    N = 30
+    xref = g["lf_zam_n30_xref"][3]
+    d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref, sc.static_obstacle)
+    w = nlp.pack(g["lf_zam_n30_U"][3], g["lf_zam_n30_X"][3])
+    assert ipm.kkt_error(d, w)[0] < 1e-7
+    r = ipm.solve(d, nlp.pack(np.zeros((N, 2)), np.tile(xref[0], (N + 1, 1))))
+    assert np.abs(r["w"] - w).max() < 1e-6
+
+
+def test_reference_window_rule_q8():
+    T, N = 70, 10
+    path = np.stack([np.arange(T, dtype=float), np.arange(T, dtype=float) * 2], axis=1)
+    orient = np.arange(T, dtype=float) * 0.01
+    x = np.arange(5, dtype=float)
+    w = nlp.reference_window(5, x, N, T, path, orient, 7.0)
+    assert w.shape == (N + 1, 5) and np.all(w[0] == x)
+    assert np.all(w[1:, 0] == np.arange(6, 16)) and np.all(w[1:, 3] == 7.0) and np.all(w[1:, 2] == 0.0)
+    w = nlp.reference_window(65, x, N, T, path, orient, 7.0)     # i >= T - N: frozen at path[60:70]
+    assert np.all(w[1:, 0] == np.arange(60, 70))
+    w30 = nlp.reference_window(0, x, 30, 30, path[:30], orient[:30], 7.0)   # N == T: path[0:30] at every step
+    assert np.all(w30[1:, 0] == np.arange(0, 30))
