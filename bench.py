@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""bench.py -- MPC solves/sec on BASELINE.json's configs[1] (ZAM_Over-1_1 lane following, batch 1024 perturbed x0, N=30).
+
+One "step" = one pass of the hot path over one batch: `mpcb200_solve` (ONE fused kernel launch that runs every SQP
+iteration of its 1024 NLPs) on inputs already resident in HBM.  `value` = solves/s over all ranks (weak scaling: every
+rank owns its own 1024 instances, no data-path collective).  `e2e` = the same metric through the public host-buffer call
+`B200Optimizer.solve_batch_host` (pinned host arrays, H2D + solve + D2H inside the timed region).
+
+  python bench.py [--gpus N --steps K --warmup W]          product arm (N>1 under torchrun, one rank per GPU)
+  python bench.py --impl reference [...]                   reference arm: the CPU restatement of the reference path (oracle/)
+                                                           on all host cores, bounded sample per step
+"""
+import argparse
+import json
+import os
+
+# the CPU legs run one single-threaded oracle process per core; keep BLAS/OpenMP from oversubscribing them
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENARIO, N_HORIZON, BATCH, SEED = "ZAM_Over-1_1_LF", 30, 1024, 20261017
+METRIC = "MPC solves/sec (N=30, 5-state kinematic bicycle) at batch 1024"
+
+
+def bytes_iter(N):
+    """Algorithmic bytes per problem per SQP iteration (SURVEY.md 8d / DESIGN.md): 4*(219N + 65)."""
+    return 4 * (219 * N + 65)
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle) leg
+def _oracle_one(args):
+    name, N, xref, X, U = args
+    import mpc_b200
+    from oracle import nlp, ipm
+    sc = mpc_b200.load_scenario(name)
+    d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref, sc.static_obstacle)
+    r = ipm.solve(d, nlp.pack(U, X))
+    return r["status"], r["iters"]
+
+
+def cpu_oracle_rate(n_sample, cores, pool=None):
+    """Times the float64 oracle on the first n_sample instances of the workload over `cores` processes."""
+    import multiprocessing as mp
+    import mpc_b200
+    sc, x0, xref, X, U = mpc_b200.make_batch(SCENARIO, n_sample, N_HORIZON, SEED)
+    jobs = [(SCENARIO, N_HORIZON, xref[b], X[b], U[b]) for b in range(n_sample)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+        pool.map(_oracle_one, jobs[:cores])          # warm the workers (imports)
+    t0 = time.perf_counter()
+    res = pool.map(_oracle_one, jobs, chunksize=max(1, n_sample // (4 * cores)))
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+    ok = sum(1 for s, _ in res if s == 1)
+    return n_sample / dt, dt, ok
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restated: oracle/), all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_sample = max(cores, min(BATCH, 4 * cores))
+    import mpc_b200
+    sc, x0, xref, X, U = mpc_b200.make_batch(SCENARIO, n_sample, N_HORIZON, SEED)
+    jobs = [(SCENARIO, N_HORIZON, xref[b], X[b], U[b]) for b in range(n_sample)]
+    pool = mp.get_context("fork").Pool(cores)
+    pool.map(_oracle_one, jobs[:cores])
+    for _ in range(args.warmup):
+        pool.map(_oracle_one, jobs)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        pool.map(_oracle_one, jobs)
+        times.append(time.perf_counter() - t0)
+    pool.close()
+    total = sum(times)
+    value = n_sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{SCENARIO} batch={BATCH} perturbed x0 N={N_HORIZON} (BASELINE configs[1])",
+                   "sample": f"first {n_sample} of the {BATCH} instances per step"},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} instances per step x {args.steps} steps, float64 oracle (oracle/ipm.py), "
+                                   f"multiprocessing.Pool({cores})"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ product arm
+def run_product(args):
+    import torch
+    import mpc_b200
+    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+        local = 0
+    dev = torch.device("cuda", local)
+    N, B = N_HORIZON, BATCH
+    # weak scaling: every rank owns B instances of its own (seed + rank); no data-path collective
+    sc, x0, xref, X0, U0 = mpc_b200.make_batch(SCENARIO, B, N, SEED + rank)
+    opt = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=args.precision,
+                        hessian=args.hessian, max_batch=B, device=local)
+    f64 = torch.float64
+    d_xref = torch.as_tensor(xref, device=dev)
+    d_X0, d_U0 = torch.as_tensor(X0, device=dev), torch.as_tensor(U0, device=dev)
+    d_X, d_U = d_X0.clone(), d_U0.clone()
+    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    d_iters = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
+    h, stream = opt.handle, torch.cuda.current_stream(dev)
+
+    def step():
+        h.check(h.lib.mpcb200_solve(h.h, d_xref.data_ptr(), d_X.data_ptr(), d_U.data_ptr(), d_status.data_ptr(),
+                                    d_iters.data_ptr(), B, stream.cuda_stream))
+
+    def reset():
+        d_X.copy_(d_X0); d_U.copy_(d_U0)
+        flush.fill_(1.0)                     # evict L2 between timed iterations
+
+    for _ in range(max(args.warmup, 3)):
+        reset(); step()
+    torch.cuda.synchronize(dev)
+    status = d_status.cpu().numpy(); iters = d_iters.cpu().numpy()
+    n_ok = int((status == 1).sum())
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    n0 = h.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s_, e_ in ev:
+        reset()
+        s_.record(stream); step(); e_.record(stream)
+    torch.cuda.synchronize(dev)
+    if dist:
+        dist.barrier()
+    launches = h.launch_count - n0
+    ms = np.array([s_.elapsed_time(e_) for s_, e_ in ev])
+    total_ms = float(ms.sum())
+    if dist:
+        t = torch.tensor([total_ms], device=dev, dtype=f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    # ---- end-to-end through the public host-buffer API (pinned host memory, H2D + solve + D2H per step)
+    hx = torch.as_tensor(xref).pin_memory(); hX0 = torch.as_tensor(X0).pin_memory(); hU0 = torch.as_tensor(U0).pin_memory()
+    hX, hU = hX0.clone().pin_memory(), hU0.clone().pin_memory()          # in/out buffers (warm start in, solution out)
+    for _ in range(2):
+        hX.copy_(hX0); hU.copy_(hU0)
+        opt.solve_batch_host(hx.numpy(), hX.numpy(), hU.numpy(), inplace=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    n1 = h.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hX.copy_(hX0); hU.copy_(hU0)
+        Ue, Xe, ste, ite = opt.solve_batch_host(hx.numpy(), hX.numpy(), hU.numpy(), inplace=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    launches += h.launch_count - n1
+    if dist:
+        t = torch.tensor([e2e_s], device=dev, dtype=f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes of one launch / its mean duration
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs, burst)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    alg_bytes = float(iters.sum()) * bytes_iter(N)
+    launch_ms = total_ms / args.steps
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
+        traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only at N=1
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = max(cores, min(BATCH, 16 * cores))
+        rate, dt, ok = cpu_oracle_rate(n_sample, cores)
+        cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_sample} of the {BATCH} instances, float64 oracle (oracle/ipm.py), Pool({cores}), {dt:.1f} s, {ok} converged"}
+    nx, nu = 5 * (N + 1), 2 * N
+    line = {
+        "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "solves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "p50_ms_per_step": float(np.median(ms)), "p50_ms_per_solve": float(np.median(ms)) / B,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{SCENARIO} batch={B} perturbed x0 (seed {SEED}+rank) N={N} cold start (BASELINE configs[1])",
+                   "parallelism": f"batch-shard x{world} (independent NLPs, no data-path collective)",
+                   "l2": "256 MB flush write between timed iterations", "hessian": args.hessian,
+                   "converged": f"{n_ok}/{B}", "mean_sqp_iters": float(iters.mean()), "max_sqp_iters": int(iters.max())},
+        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": B * (2 * nx + nu) * 8,
+                "d2h_bytes_per_step": B * (nx + nu) * 8 + B * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "mpc_solve_kernel",
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "algorithmic bytes = sum over problems of SQP iterations x 4(219N+65) B (KKT slab staged once per iteration); "
+                             "the fused kernel keeps the slab in shared memory, so real DRAM traffic is far below this"},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--hessian", default="exact", choices=["exact", "gn"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,7 +58,7 @@ struct ProbState {
   T a0_lo, a0_hi;     // stage-0 friction box (constants of the pinned stage)
   T kkt;              // last step inf-norm (diagnostic)
   T d_al, d_ap, d_ad, d_c1, d_dphi; int d_blk;   // diagnostics of the last iteration
-  int status, iters, done, nfail;
+  int status, iters, done, nfail, nsoc;
 };
 
 // ------------------------------------------------------------------ math wrappers
@@ -89,6 +89,11 @@ MPC_HD void m_sincos(double x, double* s, double* c) {
 #endif
 }
 template <typename T> MPC_HD bool m_finite(T x) { return (x - x) == T(0); }
+MPC_HD float m_eps(float) { return 6e-8f; }
+MPC_HD double m_eps(double) { return 1.2e-16; }
+// |r| with a dead zone at the rounding level of the distance h it was computed from: the slack residual of a far,
+// inactive obstacle row (lane following: dummy obstacle ~130 m away, quirk Q11) is pure rounding noise of h.
+template <typename T> MPC_HD T m_resid(T r, T h) { return m_max(m_abs(r) - T(8) * m_eps(T(0)) * h, T(0)); }
 // slack of a bound row computed from the primal value; floored at a few ulps of the bound so that an iterate that
 // rounds onto its bound (fp32: mu/nu can be below one ulp of x) gives a stiff but finite barrier weight.
 MPC_HD float m_slack(float x) { return fmaxf(x, 2.5e-7f); }
@@ -211,7 +216,7 @@ struct Solver {
   // (IPOPT's bound_push idea) and initialises slacks/duals on the central path.
   MPC_HD void init(ProbState<T>& st) const {
     const int N = P.N;
-    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.kkt = T(0);
+    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.kkt = T(0);
     const T de0 = xa(0, 2), v0 = xa(0, 3);
     const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
     bool bad = false;
@@ -506,7 +511,7 @@ struct Solver {
         const T s = S(k, j);
         const T r = (h - P.r_sum) - s;
         const T ds = gx * nx[0] + gy * nx[1] + gp * nx[4] + r;
-        o.c1 += m_abs(r);
+        o.c1 += m_resid(r, h);
         row_limits(s, V(k, V_OB0 + j), ds, mu, tau, o);
       }
       // store the step in place of the gains of this stage (dead from here on)
@@ -523,7 +528,11 @@ struct Solver {
   // ---------------------------------------------------------------- merit difference phi(alpha) - phi(0)
   // dphi: cost + barrier difference (computed term by term, no cancellation); c1: l1 infeasibility at the trial point;
   // nz: magnitude sum of the terms (for the rounding-noise allowance); returns false if a slack would leave the interior.
-  MPC_HD bool trial(const ProbState<T>& st, T al, T& dphi, T& c1, T& nz) const {
+  // reshoot = true: second-order correction.  Instead of the linear step x + al*dx the trial states are re-simulated
+  // from the trial controls, x^_{k+1} = x^_k + dt f(x^_k, u_k + al*du_k) - (1 - al) d_k, so the dynamics defects shrink
+  // EXACTLY by (1 - al) and the l1 merit cannot reject a good Newton step because of second-order defect growth (Maratos
+  // effect).  The re-simulated step overwrites DX so that commit() applies it.
+  MPC_HD bool trial(const ProbState<T>& st, T al, T& dphi, T& c1, T& nz, bool reshoot = false) const {
     const int N = P.N;
     const T mu = st.mu;
     dphi = T(0); c1 = T(0); nz = T(0);
@@ -550,12 +559,30 @@ struct Solver {
         const T xd = X(k + 1, j);
         x1a[j] = xd + xr(k + 1, j);
         xbd[j] = xd + dxb[j];
-        xba[j] = xbd[j] + xr(k + 1, j);
       }
       T d[5];
-      defect(k, xad, xbd, xaa[3], ta, nu0, nu1, d);
+      if (reshoot) {
+        // current defect of this stage (old point), then place x^_{k+1} so that the new defect is (1 - al) * d_old
+        T x0d[5], x1d[5], dold[5];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) c1 += m_abs(d[j]);
+        for (int j = 0; j < 5; ++j) { x0d[j] = X(k, j); x1d[j] = X(k + 1, j); }
+        Trig t0; t0.sn = TR(k, 0); t0.cs = TR(k, 1); t0.tn = TR(k, 2);
+        defect(k, x0d, x1d, x0d[3] + xr(k, 3), t0, u0, u1, dold);
+        T zero[5] = {T(0), T(0), T(0), T(0), T(0)};
+        T roll[5];
+        defect(k, xad, zero, xaa[3], ta, nu0, nu1, roll);      // = xt^_k + dt f(x^_k, u^_k) + c_k
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          xbd[j] = roll[j] - (T(1) - al) * dold[j];
+          dxb[j] = xbd[j] - x1d[j];
+          DX(k, j) = dxb[j] / al;
+          d[j] = (T(1) - al) * dold[j];
+        }
+      } else {
+        defect(k, xad, xbd, xaa[3], ta, nu0, nu1, d);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { xba[j] = xbd[j] + xr(k + 1, j); c1 += m_abs(d[j]); }
       // cost difference (exact, no cancellation)
       {
         const T t0 = P.R[0] * du0 * (T(2) * u0 + du0), t1 = P.R[1] * du1 * (T(2) * u1 + du1);
@@ -589,7 +616,7 @@ struct Solver {
         const T ds = al * (gx * DX(k, 0) + gy * DX(k, 1) + gp * DX(k, 4) + r);
         lrow(ds, s);
         T hb, g1, g2, g3; obst(j, xba[0], xba[1], tb.sn, tb.cs, hb, g1, g2, g3);
-        c1 += m_abs((hb - P.r_sum) - (s + ds));
+        c1 += m_resid((hb - P.r_sum) - (s + ds), hb);
       }
 #pragma unroll
       for (int j = 0; j < 5; ++j) { xad[j] = xbd[j]; xaa[j] = xba[j]; }
@@ -672,15 +699,26 @@ struct Solver {
       if (need > st.rho) st.rho = need * T(1.5) + T(1);
     }
     const T slope = f.dphi - st.rho * f.c1;
-    const T epsm = (sizeof(T) == 4) ? T(6e-8) : T(1.2e-16);
+    const T epsm = m_eps(T(0));
     T al = f.a_p;
     bool accepted = false;
     for (int t = 0; t < P.ls_max; ++t) {
       T dphi, c1, nz;
-      const bool ok = trial(st, al, dphi, c1, nz);
-      const T dm = dphi + st.rho * (c1 - f.c1);
-      const T noise = T(8) * epsm * (nz + st.rho * f.mag);
+      bool ok = trial(st, al, dphi, c1, nz);
+      T dm = dphi + st.rho * (c1 - f.c1);
+      T noise = T(8) * epsm * (nz + st.rho * f.mag);
+#ifdef MPC_DEBUG_LS
+      printf("      ls t=%d al=%.3e ok=%d dphi=%.4e c1=%.4e (c1_0 %.4e) dm=%.4e thresh=%.4e noise=%.3e nz=%.3e mag=%.3e\n", t, (double)al, (int)ok,
+             (double)dphi, (double)c1, (double)f.c1, (double)dm, (double)(T(1e-4) * al * slope + noise), (double)noise, (double)nz, (double)f.mag);
+#endif
       if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; break; }
+      if (t == 0 && ok && m_finite(dm)) {
+        // second-order correction (see trial): re-simulate the states from the trial controls
+        ok = trial(st, al, dphi, c1, nz, true);
+        dm = dphi + st.rho * (c1 - f.c1);
+        noise = T(8) * epsm * (nz + st.rho * f.mag);
+        if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; st.nsoc++; break; }
+      }
       al *= T(0.5);
     }
     if (!accepted) {

@@ -225,11 +225,16 @@ class B200Optimizer(_Base):
         h.check(h.lib.mpcb200_sqp_end(h.h, X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), s))
         return U, X, status, iters
 
-    def solve_batch_host(self, xref, X_init, U_init):
-        """End-to-end call with HOST numpy buffers (H2D + solve + D2H inside the library, synchronous)."""
+    def solve_batch_host(self, xref, X_init, U_init, inplace=False):
+        """End-to-end call with HOST numpy buffers (H2D + solve + D2H inside the library, synchronous).
+        inplace=True: X_init/U_init (C-contiguous float64, ideally pinned) are overwritten with the solution."""
         xref = np.ascontiguousarray(xref, np.float64)
-        X = np.ascontiguousarray(X_init, np.float64).copy()
-        U = np.ascontiguousarray(U_init, np.float64).copy()
+        if inplace:
+            X, U = X_init, U_init
+            assert X.flags.c_contiguous and U.flags.c_contiguous and X.dtype == np.float64 and U.dtype == np.float64
+        else:
+            X = np.ascontiguousarray(X_init, np.float64).copy()
+            U = np.ascontiguousarray(U_init, np.float64).copy()
         B = xref.shape[0]
         status = np.empty(B, np.int32)
         iters = np.empty(B, np.int32)

@@ -4,6 +4,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cmath>
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/config_params.h"
 
 using namespace mpcb200;
@@ -27,6 +28,12 @@ static void run(const mpcb200_config& cfg, const double* xref, double* Xio, doub
     S.init(st);
     for (int it = 0; it < cfg.max_iter && !st.done; ++it) {
       S.iterate(st);
+      if (trace == 2) {
+        int bk = 0, bj = 0; double bv = 0;
+        for (int k = 0; k < N; ++k) for (int j = 0; j < 7; ++j) { double v = fabs((double)S.DX(k, j)); if (v > bv) { bv = v; bk = k; bj = j; } }
+        printf("   max step comp: stage %d comp %d val %.3e | du0 %.3e %.3e | dx_N %.2e %.2e %.2e %.2e %.2e\n", bk, bj, bv, (double)S.DU(0,0), (double)S.DU(0,1),
+               (double)S.DX(N-1,0),(double)S.DX(N-1,1),(double)S.DX(N-1,2),(double)S.DX(N-1,3),(double)S.DX(N-1,4));
+      }
       if (trace) printf("it %3d mu %.2e step %.3e rho %.2e al %.3e ap %.3e ad %.3e c1 %.3e dphi %.3e blk %d/%d status %d\n", st.iters, (double)st.mu, (double)st.kkt, (double)st.rho, (double)st.d_al, (double)st.d_ap, (double)st.d_ad, (double)st.d_c1, (double)st.d_dphi, st.d_blk / 16, st.d_blk % 16, st.status);
     }
     S.store(xr, Xb, Ub);

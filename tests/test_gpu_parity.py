@@ -1,0 +1,184 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI (libmpcb200.so via ctypes);
+the oracle is only the checker.  Tolerances: fp32 arithmetic ||dU||inf, ||dX||inf <= 1e-3 (rad/s, m/s^2, m, rad, m/s);
+fp64 arithmetic <= 1e-6."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"f32": 1e-3, "f64": 1e-6}
+
+
+def _opt(name, N, precision="f32", hessian="exact", max_batch=4096, **kw):
+    import torch
+    import mpc_b200
+    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
+    assert torch.cuda.is_available()
+    sc = mpc_b200.load_scenario(name)
+    return sc, B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=precision, hessian=hessian,
+                             max_batch=max_batch, **kw)
+
+
+def _np(*ts):
+    return [t.cpu().numpy() for t in ts]
+
+
+@pytest.mark.parametrize("key,name,N", [("lf_zam_n30", "ZAM_Over-1_1_LF", 30), ("lf_lanker_n50", "USA_Lanker-2_18_T-1_LF", 50),
+                                         ("lf_zam_n10", "ZAM_Over-1_1_LF", 10)])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("hessian", ["gn", "exact"])
+def test_solve_matches_oracle_golden(key, name, N, precision, hessian):
+    g = np.load(os.path.join(G, "nlp_solutions.npz"))
+    sc, opt = _opt(name, N, precision, hessian, max_batch=64)
+    xref = g[key + "_xref"]
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert (st == 1).all(), st
+    assert np.abs(U - g[key + "_U"]).max() < TOL[precision]
+    assert np.abs(X - g[key + "_X"]).max() < TOL[precision]
+    assert opt.handle.launch_count == 1          # one fused launch ran every SQP iteration
+
+
+def test_step0_known_answer_both_weight_sets():
+    for name in ("ZAM_Over-1_1_LF", "ZAM_Over-1_1_CA"):
+        sc, opt = _opt(name, 10, "f32", max_batch=8)
+        xref = np.tile(sc.x0, (1, 11, 1))
+        U, X, st, it = _np(*opt.solve_batch(xref))
+        assert st[0] == 1 and abs(U[0, 0, 1] + np.sqrt(11.5)) < 1e-4 and abs(U[0, 0, 0]) < 1e-4
+
+
+def test_live_oracle_config2_sample_and_full_batch_properties():
+    """BASELINE config 2 at full size (B=1024, N=30): live oracle on a sample + size-independent properties on all."""
+    import mpc_b200
+    from oracle import nlp, ipm
+    N, B = 30, 1024
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=B)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 20261017)
+    U, X, st, it = _np(*opt.solve_batch(xref, X0, U0))
+    assert (st == 1).all(), np.unique(st, return_counts=True)
+    assert it.max() <= 40
+    # dynamics defects, pinned stage, bounds (properties of any solution of the reference NLP)
+    xn = nlp.euler_step(X[:, :-1], U, sc.dt)
+    assert np.abs(xn - X[:, 1:]).max() < 2e-4
+    assert np.array_equal(X[:, 0], xref[:, 0])
+    assert U[:, :, 0].min() >= -0.4 - 1e-6 and U[:, :, 0].max() <= 0.4 + 1e-6 and U[:, :, 1].max() <= 11.5 + 1e-6
+    assert X[:, :, 3].min() >= -1e-6 and np.abs(X[:, :, 2]).max() <= 1.066 + 1e-6
+    s0 = x0[:, 3] ** 2 * np.tan(x0[:, 2]) / 2.578
+    assert (np.abs(U[:, 0, 1] ** 2 + s0) <= 11.5 + 1e-4).all()                      # friction row (Q3)
+    for b in (0, 17, 511, 1023):
+        d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+        r = ipm.solve(d, nlp.pack(U0[b], X0[b]))
+        Uo, Xo = nlp.split(r["w"], N)
+        assert r["status"] == 1
+        assert np.abs(U[b] - Uo).max() < 1e-3 and np.abs(X[b] - Xo).max() < 1e-3
+
+
+def test_stepwise_launches_equal_fused_launch():
+    import mpc_b200
+    N, B = 30, 96
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=128)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 3)
+    U1, X1, st1, it1 = _np(*opt.solve_batch(xref, X0, U0))
+    n0 = opt.handle.launch_count
+    U2, X2, st2, it2 = _np(*opt.solve_batch_stepwise(xref, X0, U0, n_iter=int(it1.max()) + 2))
+    assert opt.handle.launch_count - n0 == int(it1.max()) + 4       # begin + n_iter + end
+    assert np.array_equal(st1, st2) and np.array_equal(it1, it2)
+    assert np.array_equal(U1, U2) and np.array_equal(X1, X2)          # bit-identical: same arithmetic, slab round-trips via TMA
+
+
+def test_ragged_and_tiny_batches_and_host_path():
+    import mpc_b200
+    N = 30
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=256)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", 101, N, 11)
+    Ufull, Xfull, stf, itf = _np(*opt.solve_batch(xref, X0, U0))
+    for B in (1, 31, 33, 101):
+        U, X, st, it = _np(*opt.solve_batch(xref[:B], X0[:B], U0[:B]))
+        assert np.array_equal(U, Ufull[:B]) and np.array_equal(X, Xfull[:B]) and np.array_equal(st, stf[:B])
+    Uh, Xh, sth, ith = opt.solve_batch_host(xref, X0, U0)
+    assert np.array_equal(Uh, Ufull) and np.array_equal(Xh, Xfull) and np.array_equal(sth, stf) and np.array_equal(ith, itf)
+    import torch
+    e = opt.solve_batch(torch.zeros(0, N + 1, 5, dtype=torch.float64, device="cuda"))      # empty batch is a no-op
+    assert e[0].shape[0] == 0
+
+
+def test_infeasible_pinned_stage_is_flagged_not_fatal():
+    sc, opt = _opt("ZAM_Over-1_1_LF", 10, "f32", max_batch=8)
+    x_bad = sc.x0.copy()
+    x_bad[2] = 0.5
+    xref = np.stack([np.tile(sc.x0, (11, 1)), np.tile(x_bad, (11, 1))])
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert st[0] == 1 and st[1] == -8
+
+
+def test_collision_avoidance_kkt_points_config3_sample():
+    """Config 3 (obstacle constraints).  From a cold start the NLP has several local minima, so parity is stated as:
+    the GPU point is a KKT point of the reference NLP, keeps the 3.3 m clearance, and the oracle warm-started there stays."""
+    import mpc_b200
+    from oracle import nlp, ipm
+    N, B = 30, 64
+    sc, opt = _opt("ZAM_Over-1_1_CA", N, "f64", max_batch=B, max_iter=200)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_CA", B, N, 20261018)
+    U, X, st, it = _np(*opt.solve_batch(xref, X0, U0))
+    assert (st == 1).all(), (st, it)
+    for b in (0, 5, 63):
+        d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+        w = nlp.pack(U[b], X[b])
+        assert ipm.kkt_error(d, w)[0] < 1e-6
+        assert (nlp.g_fun(d, w)[1 + 5 * (N + 1):] >= d.r_sum - 1e-7).all()
+        r = ipm.solve(d, w)
+        assert r["status"] == 1 and np.abs(r["w"] - w).max() < 1e-5
+    # fp32 arithmetic reaches the same points
+    sc, opt32 = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=200)
+    U32, X32, st32, _ = _np(*opt32.solve_batch(xref, X0, U0))
+    ok = st32 == 1
+    assert ok.mean() > 0.9
+    assert np.abs(U32[ok] - U[ok]).max() < 1e-3 and np.abs(X32[ok] - X[ok]).max() < 1e-3
+
+
+def test_plant_step_shift_and_ref_window_kernels():
+    import torch
+    import mpc_b200
+    from oracle import nlp
+    N, B = 10, 37
+    sc, opt = _opt("USA_Lanker-2_18_T-1_LF", N, "f32", max_batch=64)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(B, 5)); x[:, 3] += 8
+    U = rng.normal(size=(B, N, 2)) * 0.2
+    X = rng.normal(size=(B, N + 1, 5))
+    xd, Ud, Xd = opt._dev(x).clone(), opt._dev(U).clone(), opt._dev(X).clone()
+    ua = opt.plant_step_shift(xd, Ud, Xd)
+    assert np.array_equal(ua.cpu().numpy(), U[:, 0])
+    assert np.abs(xd.cpu().numpy() - nlp.euler_step(x, U[:, 0], sc.dt)).max() < 1e-13
+    assert np.array_equal(Ud.cpu().numpy(), np.concatenate([U[:, 1:], U[:, -1:]], axis=1))
+    assert np.array_equal(Xd.cpu().numpy(), np.concatenate([X[:, 1:], X[:, -1:]], axis=1))
+    for i in (0, 7, 59, 60, 69):
+        w = opt.build_ref_window(i, opt._dev(x)).cpu().numpy()
+        assert np.array_equal(w, mpc_b200.reference_window(i, x, N, sc.iter_length, sc.reference_path, sc.orientation, sc.desired_velocity))
+
+
+def test_closed_loop_on_device_matches_oracle_closed_loop():
+    """The reference's whole optimize() loop (optimizer.py:562-643), noise-free, N=10, T=30: device loop vs the oracle
+    run with the same loop on the host, plus the reference-contract optimize() (B=1)."""
+    import mpc_b200
+    from mpc_b200.optimizer import make_configuration, init_values_from_state, B200Optimizer
+    from oracle import closed_loop
+    N = 10
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f64", max_batch=32)
+    traj_o, u_o = closed_loop.optimize(sc, N)
+    x0 = np.tile(sc.x0, (3, 1))
+    traj, ctrl, st, it = opt.optimize_batch(x0)
+    assert (st == 1).all()
+    assert np.abs(traj[0] - traj_o).max() < 1e-5 and np.abs(ctrl[0] - u_o).max() < 1e-5
+    assert np.array_equal(traj[0], traj[2])
+    # recorded-fixture bands: step-0 braking at the friction limit, end speed of the noise-free replay
+    assert abs(ctrl[0, 0, 1] + np.sqrt(11.5)) < 1e-6 and abs(traj[0, -1, 3] - 17.41) < 0.05
+    ts, us, tv = opt.optimize()
+    assert ts.shape == (30, 5) and us.shape == (30, 2) and tv.shape == (30,)
+    assert np.abs(ts - traj_o).max() < 1e-5 and np.abs(us - u_o).max() < 1e-5
+    # fp32 arithmetic over the whole closed loop
+    sc, opt32 = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=32)
+    t32, c32, st32, _ = opt32.optimize_batch(x0[:1])
+    assert np.abs(t32[0] - traj_o).max() < 5e-3 and np.abs(c32[0] - u_o).max() < 5e-3

@@ -1,0 +1,134 @@
+"""CPU tests of the host side and of the solver core's ALGORITHM (tests/host_sim = the device code of the CUDA kernels
+compiled with g++; test tooling only -- the product has no CPU path)."""
+import os
+
+import numpy as np
+import pytest
+
+import hostsim
+import mpc_b200
+from mpc_b200 import optimizer as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cfg(sc, N, prec, hess=1):
+    circles, r_sum, off = O.obstacle_circles_and_radius(sc.static_obstacle)
+    cfg = hostsim.default_config(N, prec)
+    cfg.hessian = hess
+    cfg.dt = sc.dt
+    w = sc.weights_setting
+    for i, k in enumerate(("weight_x", "weight_y", "weight_steering_angle", "weight_velocity", "weight_heading_angle")):
+        cfg.Q[i] = w[k]
+    cfg.R[0], cfg.R[1] = w["weight_velocity_steering_angle"], w["weight_long_acceleration"]
+    cfg.r_sum, cfg.ego_offset = r_sum, off
+    for j in range(3):
+        cfg.obstacle[2 * j], cfg.obstacle[2 * j + 1] = circles[j]
+    return cfg
+
+
+@pytest.mark.parametrize("key,name,N", [("lf_zam_n30", "ZAM_Over-1_1_LF", 30), ("lf_lanker_n50", "USA_Lanker-2_18_T-1_LF", 50),
+                                         ("lf_zam_n10", "ZAM_Over-1_1_LF", 10)])
+@pytest.mark.parametrize("prec,tol", [(0, 1e-3), (1, 1e-6)])
+@pytest.mark.parametrize("hess", [0, 1])
+def test_solver_core_matches_oracle_golden(key, name, N, prec, tol, hess):
+    g = np.load(os.path.join(G, "nlp_solutions.npz"))
+    sc = mpc_b200.load_scenario(name)
+    xref = g[key + "_xref"]
+    B = xref.shape[0]
+    X0 = np.repeat(xref[:, :1, :], N + 1, axis=1)
+    X, U, st, it, _ = hostsim.solve(_cfg(sc, N, prec, hess), xref, X0, np.zeros((B, N, 2)))
+    assert (st == 1).all(), st
+    assert np.abs(U - g[key + "_U"]).max() < tol        # ||dU||inf  (rad/s, m/s^2)
+    assert np.abs(X - g[key + "_X"]).max() < tol        # ||dX||inf  (m, rad, m/s)
+
+
+def test_solver_core_step0_known_answer():
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    N = 10
+    xref = np.tile(sc.x0, (1, N + 1, 1))
+    for prec, tol in ((0, 1e-4), (1, 1e-7)):
+        X, U, st, it, _ = hostsim.solve(_cfg(sc, N, prec), xref, xref, np.zeros((1, N, 2)))
+        assert st[0] == 1
+        assert abs(U[0, 0, 1] + np.sqrt(11.5)) < tol and abs(U[0, 0, 0]) < 1e-4
+
+
+def test_solver_core_flags_infeasible_pinned_stage():
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    N = 10
+    x0 = sc.x0.copy()
+    x0[2] = 0.5          # v0^2 tan(delta0)/2.578 = 84 > a_max: friction row infeasible (quirk Q3)
+    xref = np.tile(x0, (1, N + 1, 1))
+    _, _, st, _, _ = hostsim.solve(_cfg(sc, N, 1), xref, xref, np.zeros((1, N, 2)))
+    assert st[0] == -8
+
+
+def test_collision_avoidance_solution_is_a_kkt_point_of_the_reference_nlp():
+    from oracle import nlp, ipm
+    N, B = 30, 3
+    sc, x0, xref, X, U = mpc_b200.make_batch("ZAM_Over-1_1_CA", B, N, 20261018)
+    Xs, Us, st, it, _ = hostsim.solve(_cfg(sc, N, 1), xref, X, U)
+    assert (st == 1).all()
+    for b in range(B):
+        d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+        w = nlp.pack(Us[b], Xs[b])
+        assert ipm.kkt_error(d, w)[0] < 1e-6
+        assert (nlp.g_fun(d, w)[1 + 5 * (N + 1):] >= d.r_sum - 1e-7).all()      # keeps >= 3.3 m from the obstacle
+        r = ipm.solve(d, w)                                                      # oracle warm-started at that point
+        assert r["status"] == 1 and np.abs(r["w"] - w).max() < 1e-5
+
+
+def test_scenarios_and_batch_generator():
+    names = mpc_b200.scenario_names()
+    assert {"ZAM_Over-1_1_LF", "ZAM_Over-1_1_CA", "USA_Lanker-2_18_T-1_LF"} <= set(names)
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    assert sc.iter_length == 30 and abs(sc.desired_velocity - 19.9991) < 1e-9 and sc.dt == 0.1
+    assert np.allclose(sc.reference_path[0], [29.9948, -1.1501]) and np.allclose(sc.reference_path[-1], [87.8, 3.3])
+    assert mpc_b200.load_scenario("USA_Lanker-2_18_T-1_LF").iter_length == 70
+    a = mpc_b200.make_batch("ZAM_Over-1_1_LF", 64, 30, 20261017)
+    b = mpc_b200.make_batch("ZAM_Over-1_1_LF", 64, 30, 20261017)
+    assert np.array_equal(a[1], b[1]) and a[2].shape == (64, 31, 5)
+    x0 = a[1]
+    assert (np.abs(x0[:, 2]) <= 0.05).all() and (x0[:, 3] >= 1).all() and (x0[:, 3] <= 25).all()
+    assert np.array_equal(a[2][:, 0], x0) and np.allclose(a[2][:, 1:, :2], sc.reference_path[None])
+    ca = mpc_b200.make_batch("ZAM_Over-1_1_CA", 256, 30, 20261018)
+    circles, r_sum, off = O.obstacle_circles_and_radius(ca[0].static_obstacle)
+    assert abs(r_sum - 3.3) < 1e-12 and off == 0.75
+    with pytest.raises(ValueError):
+        mpc_b200.make_batch("ZAM_Over-1_1_LF", 4, 31, 1)
+
+
+def test_reference_window_matches_oracle_rule():
+    from oracle import nlp
+    sc = mpc_b200.load_scenario("USA_Lanker-2_18_T-1_LF")
+    x = np.array([[1.0, 2.0, 0.1, 5.0, 0.3], [0.0, 0.0, 0.0, 6.0, -0.4]])
+    for i in (0, 5, 19, 20, 21, 60, 69):
+        for N in (10, 50):
+            w = mpc_b200.reference_window(i, x, N, sc.iter_length, sc.reference_path, sc.orientation, sc.desired_velocity)
+            for b in range(2):
+                assert np.array_equal(w[b], nlp.reference_window(i, x[b], N, sc.iter_length, sc.reference_path, sc.orientation,
+                                                                 sc.desired_velocity))
+
+
+def test_optimizer_base_mirrors_reference_attributes():
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_CA")
+    conf = O.make_configuration(sc, 30)
+    base = O.OptimizerBase(conf, O.init_values_from_state(sc.x0), 30)
+    assert (base.delta_min, base.delta_max, base.deltav_min, base.deltav_max) == (-1.066, 1.066, -0.4, 0.4)
+    assert (base.v_min, base.v_max, base.a_max) == (0, 50.8, 11.5)
+    assert base.iter_length == 30 and base.predict_horizon == 30 and base.delta_t == 0.1
+    assert abs(base.radius_ego - 1.2) < 1e-12 and abs(base.radius_obstacle - 2.1) < 1e-12
+    c = base.obstacle_circles_centers_tuple
+    assert np.allclose(c[0], [59.948, 0.08323]) and np.allclose(c[1], [59.948 + np.cos(0.07759), 0.08323 + np.sin(0.07759)])
+    for m in ("equal_constraints", "inequal_constraints", "cost_function", "solver", "optimize"):
+        assert callable(getattr(base, m))
+    assert issubclass(O.B200Optimizer, O.OptimizerBase) or O._Base is not O.OptimizerBase
+
+
+def test_shard_ranges_cover_batch():
+    from mpc_b200.sharding import shard_range, shard_sizes
+    for B in (1, 7, 1024, 4097):
+        for W in (1, 2, 4, 8):
+            r = [shard_range(B, k, W) for k in range(W)]
+            assert r[0][0] == 0 and r[-1][1] == B and all(r[k][1] == r[k + 1][0] for k in range(W - 1))
+            assert sum(shard_sizes(B, W)) == B and max(shard_sizes(B, W)) - min(shard_sizes(B, W)) <= 1
