@@ -27,7 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENARIO, N_HORIZON, BATCH, SEED = "ZAM_Over-1_1_LF", 30, 1024, 20261017
+SCENARIO, N_HORIZON, BATCH, SEED = "ZAM_Over-1_1_LF", 30, int(os.environ.get("MPCB200_BENCH_BATCH", "1024")), 20261017
 METRIC = "MPC solves/sec (N=30, 5-state kinematic bicycle) at batch 1024"
 
 
@@ -279,7 +279,7 @@ def run_product(args):
                 "d2h_bytes_per_step": B * (nx + nu) * 8 + B * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "mpc_solve_kernel",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "mpc_warp_solve_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "algorithmic bytes = sum over problems of SQP iterations x 4(219N+65) B (KKT slab staged once per iteration); "
                              "the fused kernel keeps the slab in shared memory, so real DRAM traffic is far below this"},
@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--hessian", default="exact", choices=["exact", "gn"])
+    ap.add_argument("--hessian", default="gn", choices=["exact", "gn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

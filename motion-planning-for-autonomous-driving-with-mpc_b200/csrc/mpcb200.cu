@@ -1,24 +1,29 @@
 // mpcb200.cu -- sm_100a kernels + the C ABI of libmpcb200.so (include/mpcb200.h).
 //
 // Execution model (B200-first, not a translation of anything in the reference -- the reference has no GPU code):
-//   * one ego instance (one NLP) per CUDA lane; a CTA is ONE warp that owns a tile of LANES problems;
-//   * the tile's whole KKT working set ("slab": iterate, reference, multipliers, slacks, Riccati gains, step) lives in
-//     shared memory as [word][lane] so every access is bank-conflict free; it is 1303 words/problem at N = 30;
-//   * problem data moves HBM <-> shared memory with TMA bulk copies (cp.async.bulk + mbarrier): the tile's float64
-//     xref/X/U rows are one contiguous chunk each (one bulk load per array, one bulk store per output array), and in
-//     the launch-per-iteration mode the slab itself is one bulk load + one bulk store per launch;
+//   * ONE WARP PER EGO INSTANCE (one NLP); a CTA is WPC warps = WPC problems.  Inside a problem the lanes are stages
+//     (linearisation, residuals, merit, commit), entries of the 5x6 Riccati block [P | p] (KKT factor sweep) or state
+//     components (forward sweep) -- see warp_core.cuh;
+//   * the problem's whole KKT working set ("slab": iterate, reference, multipliers, slacks, stage KKT blocks, Riccati
+//     gains, step; 94N+21 words = 11.4 KB at N = 30 in fp32) lives in shared memory for the whole solve;
+//   * problem data moves HBM <-> shared memory with TMA bulk copies (cp.async.bulk + mbarrier): the CTA's float64
+//     xref/X/U rows are one contiguous chunk per array, and in the launch-per-iteration mode each warp's slab is one
+//     bulk load + one bulk store per launch;
 //   * all SQP iterations of a problem run inside one launch (problems are independent, so no grid-wide sync is ever
-//     needed); lanes that converge early idle until their warp is done;
-//   * up to 148 x (227 KB / slab) tiles are co-resident; larger batches run in waves.
+//     needed) and a warp stops as soon as ITS problem has converged;
+//   * batch 1024 = 512 CTAs x 2 warps over 148 SMs (6-8 warps per SM, every SM busy); larger batches run in waves
+//     scheduled by the hardware (up to 7 CTAs of 28.6 KB resident per SM).
 // Tensor cores are not used: the factorisation works on 5x5/2x2 stage blocks along a length-N dependency chain.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <new>
 
 #include "config_params.h"
+#include "warp_core.cuh"
 
 using namespace mpcb200;
 
@@ -64,7 +69,7 @@ struct SolveArgs {
   double* U;            // [B][N][2]
   int* status;          // [B]
   int* iters;           // [B]
-  T* slab;              // global image of the slabs [tiles][words][LANES] (stepwise mode / global-workspace mode)
+  T* slab;              // global image of the slabs [B][words] (stepwise mode)
   ProbState<T>* state;  // [B] (stepwise mode)
   T* obs_shift;         // [B][6] shifted obstacle centres (stepwise mode)
   int B;
@@ -72,138 +77,137 @@ struct SolveArgs {
   int n_iter;
 };
 
-// cooperative tile copy HBM <-> staging: one TMA bulk op for a full tile, per-lane loops for a ragged last tile
-template <int LANES>
-__device__ __forceinline__ void tile_load(double* sdst, const double* gsrc, int per_problem, int nvalid, uint64_t* bar, uint32_t& phase) {
-  const int lane = threadIdx.x;
-  if (nvalid == LANES) {
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(LANES * per_problem * sizeof(double));
-      mbar_expect_tx(bar, bytes);
-      tma_load_1d(sdst, gsrc, bytes, bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-  } else {
-    for (int i = lane; i < nvalid * per_problem; i += 32) sdst[i] = gsrc[i];
-    __syncwarp();
-  }
+// shared-memory carve-up of one CTA: [WPC slabs of T][float64 staging: xref | X | U for WPC problems]
+template <typename T, int WPC>
+struct Smem {
+  int nx, nu;
+  size_t slab_bytes;
+  unsigned char* raw;
+  __device__ Smem(unsigned char* raw_, int N, int words) : nx(5 * (N + 1)), nu(2 * N), slab_bytes((size_t)words * sizeof(T)), raw(raw_) {}
+  __device__ T* slab(int w) const { return reinterpret_cast<T*>(raw + (size_t)w * slab_bytes); }
+  __device__ double* xref(int w = 0) const { return reinterpret_cast<double*>(raw + (size_t)WPC * slab_bytes) + (size_t)w * nx; }
+  __device__ double* X(int w = 0) const { return xref(0) + (size_t)WPC * nx + (size_t)w * nx; }
+  __device__ double* U(int w = 0) const { return xref(0) + (size_t)2 * WPC * nx + (size_t)w * nu; }
+};
+static size_t smem_bytes_for(int N, int words, size_t elem, int wpc) {
+  return (size_t)wpc * ((size_t)words * elem + (size_t)(12 * N + 10) * sizeof(double));
 }
-template <int LANES>
-__device__ __forceinline__ void tile_store(double* gdst, const double* ssrc, int per_problem, int nvalid) {
-  const int lane = threadIdx.x;
-  __syncwarp();
-  if (nvalid == LANES) {
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_1d(gdst, ssrc, (uint32_t)(LANES * per_problem * sizeof(double)));
-      tma_store_commit_wait();
-    }
-    __syncwarp();
-  } else {
-    for (int i = lane; i < nvalid * per_problem; i += 32) gdst[i] = ssrc[i];
-    __syncwarp();
-  }
+
+// CTA-cooperative tile copies HBM <-> float64 staging.  A full tile whose byte count is a multiple of 16 moves as TMA
+// bulk copies (one elected thread, completion on an mbarrier / bulk group); a ragged last tile uses plain loops.
+template <int WPC>
+__device__ __forceinline__ bool tile_is_bulk(int nvalid, int per_problem) {
+  return nvalid == WPC && ((WPC * per_problem * (int)sizeof(double)) % 16) == 0;
 }
 
 // ===================================================================================================== solve kernel
-// SMEM_WS: slab in shared memory (staging aliases the K/V/S/TR block, dead during load/store); otherwise the slab is
-// the global image and shared memory only holds the float64 staging.
-template <typename T, int LANES, bool SMEM_WS>
-__global__ void __launch_bounds__(32, 1) mpc_solve_kernel(const SolveArgs<T> a) {
+// One warp per ego instance; WPC warps (problems) per CTA.  All SQP iterations of a problem run inside the launch
+// (MODE_ONESHOT), or `n_iter` of them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
+template <typename T, int WPC>
+__global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const SolveArgs<T> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
-  const int lane = threadIdx.x;
-  const int tile = blockIdx.x;
+  __shared__ __align__(8) uint64_t bar_io;
+  __shared__ __align__(8) uint64_t bar_w[WPC];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
-  const Layout L(N);
-  const int base = tile * LANES;
-  const int nvalid = min(LANES, a.B - base);
-  const bool valid = lane < nvalid;
-  const int b = base + (valid ? lane : 0);
+  const WLayout L(N);
+  const Smem<T, WPC> sm(smem_raw, N, L.words);
+  const int nx = sm.nx, nu = sm.nu;
+  const int base = blockIdx.x * WPC;
+  const int nvalid = min(WPC, a.B - base);
+  const bool valid = wid < nvalid;
+  const int b = base + (valid ? wid : 0);
 
-  T* slab_s = reinterpret_cast<T*>(smem_raw);
-  T* slab_g = a.slab ? a.slab + (size_t)tile * L.words * LANES : nullptr;
-  T* wsbase = SMEM_WS ? slab_s : slab_g;
-  double* stage = SMEM_WS ? reinterpret_cast<double*>(slab_s + (size_t)L.o_K * LANES) : reinterpret_cast<double*>(smem_raw);
-  const int nx = 5 * (N + 1), nu = 2 * N;
-  double* st_xref = stage;
-  double* st_X = stage + (size_t)LANES * nx;
-  double* st_U = st_X + (size_t)LANES * nx;
-
-  uint32_t phase = 0;
-  if (lane == 0) mbar_init(&bar, 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_io, 1);
+#pragma unroll
+    for (int i = 0; i < WPC; ++i) mbar_init(&bar_w[i], 1);
+  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
+  __syncthreads();
 
-  Ws<T, LANES> ws{wsbase + (lane < LANES ? lane : 0)};
+  const WarpCtx w;
   T obs[6];
-  Solver<T, LANES> S(a.P, ws, obs);
+  WarpSolver<T> S(a.P, sm.slab(wid), obs, w);
   ProbState<T> st;
+  const bool need_xref = (a.mode != MODE_ITER);
+  const bool need_warm = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
 
-  if (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN) {
-    tile_load<LANES>(st_xref, a.xref + (size_t)base * nx, nx, nvalid, &bar, phase);
-    tile_load<LANES>(st_X, a.X + (size_t)base * nx, nx, nvalid, &bar, phase);
-    tile_load<LANES>(st_U, a.U + (size_t)base * nu, nu, nvalid, &bar, phase);
-    if (valid) {
-      S.load(st_xref + (size_t)lane * nx, st_X + (size_t)lane * nx, st_U + (size_t)lane * nu, a.obstacle, obs);
-    }
-    __syncwarp();   // staging is dead from here; init() overwrites the aliased V/S block
-    if (valid) S.init(st); else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
-  } else {
-    // resume: bring the slab image back (TMA bulk) and the per-problem scalars
-    if (SMEM_WS) {
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t bytes = (uint32_t)((size_t)L.words * LANES * sizeof(T));
-        mbar_expect_tx(&bar, bytes);
-        tma_load_1d(slab_s, slab_g, bytes, &bar);
+  // ---- problem data in: xref (+ warm start) of the CTA's tile, HBM -> staging
+  if (need_xref) {
+    if (tile_is_bulk<WPC>(nvalid, nx) && tile_is_bulk<WPC>(nvalid, nu)) {
+      if (threadIdx.x == 0) {
+        const uint32_t bx = (uint32_t)(WPC * nx * sizeof(double)), bu = (uint32_t)(WPC * nu * sizeof(double));
+        mbar_expect_tx(&bar_io, need_warm ? (2 * bx + bu) : bx);
+        tma_load_1d(sm.xref(), a.xref + (size_t)base * nx, bx, &bar_io);
+        if (need_warm) {
+          tma_load_1d(sm.X(), a.X + (size_t)base * nx, bx, &bar_io);
+          tma_load_1d(sm.U(), a.U + (size_t)base * nu, bu, &bar_io);
+        }
       }
-      mbar_wait(&bar, phase);
-      phase ^= 1u;
+      mbar_wait(&bar_io, 0);
+    } else {
+      for (int i = threadIdx.x; i < nvalid * nx; i += 32 * WPC) {
+        sm.xref()[i] = a.xref[(size_t)base * nx + i];
+        if (need_warm) sm.X()[i] = a.X[(size_t)base * nx + i];
+      }
+      if (need_warm) for (int i = threadIdx.x; i < nvalid * nu; i += 32 * WPC) sm.U()[i] = a.U[(size_t)base * nu + i];
+      __syncthreads();
     }
+  }
+
+  if (need_warm) {
+    if (valid) { S.load(sm.xref(wid), sm.X(wid), sm.U(wid), a.obstacle, obs); S.init(st); }
+    else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
+  } else {
+    // resume: the slab image comes back by one TMA bulk copy per warp, the per-problem scalars by plain loads
     if (valid) {
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)((size_t)L.words * sizeof(T));
+        mbar_expect_tx(&bar_w[wid], bytes);
+        tma_load_1d(sm.slab(wid), a.slab + (size_t)b * L.words, bytes, &bar_w[wid]);
+      }
+      mbar_wait(&bar_w[wid], 0);
       st = a.state[b];
 #pragma unroll
       for (int j = 0; j < 6; ++j) obs[j] = a.obs_shift[(size_t)b * 6 + j];
     } else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
   }
 
-  if (a.mode != MODE_END) {
-    for (int it = 0; it < a.n_iter; ++it) {
-      if (__all_sync(0xffffffffu, st.done)) break;
-      if (!st.done) S.iterate(st);
-    }
+  if (a.mode != MODE_END && valid) {
+    for (int it = 0; it < a.n_iter && !st.done; ++it) S.iterate(st);
   }
 
   if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
-    // solution back to float64 row-major: staging needs xref again (rho is added back in float64)
-    __syncwarp();
-    tile_load<LANES>(st_xref, a.xref + (size_t)base * nx, nx, nvalid, &bar, phase);
-    if (valid) S.store(st_xref + (size_t)lane * nx, st_X + (size_t)lane * nx, st_U + (size_t)lane * nu);
-    tile_store<LANES>(a.X + (size_t)base * nx, st_X, nx, nvalid);
-    tile_store<LANES>(a.U + (size_t)base * nu, st_U, nu, nvalid);
+    // solution back to float64 row-major (rho is added back in float64), staging -> HBM
     if (valid) {
-      if (a.status) a.status[b] = st.status;
-      if (a.iters) a.iters[b] = st.iters;
-    }
-  } else {
-    // keep the slab + scalars for the next launch
-    if (SMEM_WS) {
-      __syncwarp();
-      fence_async_smem();
-      __syncwarp();
+      S.store(sm.xref(wid), sm.X(wid), sm.U(wid));
       if (lane == 0) {
-        tma_store_1d(slab_g, slab_s, (uint32_t)((size_t)L.words * LANES * sizeof(T)));
+        if (a.status) a.status[b] = st.status;
+        if (a.iters) a.iters[b] = st.iters;
+      }
+    }
+    if (tile_is_bulk<WPC>(nvalid, nx) && tile_is_bulk<WPC>(nvalid, nu)) {
+      fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tma_store_1d(a.X + (size_t)base * nx, sm.X(), (uint32_t)(WPC * nx * sizeof(double)));
+        tma_store_1d(a.U + (size_t)base * nu, sm.U(), (uint32_t)(WPC * nu * sizeof(double)));
         tma_store_commit_wait();
       }
-      __syncwarp();
+    } else {
+      __syncthreads();
+      for (int i = threadIdx.x; i < nvalid * nx; i += 32 * WPC) a.X[(size_t)base * nx + i] = sm.X()[i];
+      for (int i = threadIdx.x; i < nvalid * nu; i += 32 * WPC) a.U[(size_t)base * nu + i] = sm.U()[i];
     }
-    if (valid) {
+  } else if (valid) {
+    // keep the slab + scalars for the next launch
+    __syncwarp();
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_1d(a.slab + (size_t)b * L.words, sm.slab(wid), (uint32_t)((size_t)L.words * sizeof(T)));
+      tma_store_commit_wait();
       a.state[b] = st;
 #pragma unroll
       for (int j = 0; j < 6; ++j) a.obs_shift[(size_t)b * 6 + j] = obs[j];
@@ -223,7 +227,6 @@ struct LoopArgs {
   double* ctrl;            // [B][Tlen][2]
   int* status;             // [B][Tlen]
   int* iters;              // [B][Tlen]
-  T* slab;
   double desired_velocity;
   double l_wb, dt;
   int B, Tlen;
@@ -237,77 +240,76 @@ __device__ __forceinline__ void plant_euler(double* x, double u0, double u1, dou
   x[0] += dt * v * c; x[1] += dt * v * s; x[2] += dt * u0; x[3] += dt * u1; x[4] += dt * v / l_wb * tn;
 }
 
+// row k+1 of the X_ref block of MPC step i (desired_command_and_trajectory, optimizer.py:657-702, quirk Q8)
+__device__ __forceinline__ void ref_window_row(int i, int k, int N, int Tlen, const double* path, const double* orient, double vdes, double* r) {
+  const int idx = (i >= Tlen - N) ? (k + (Tlen - N)) : (i + k + 1);
+  r[0] = path[2 * idx]; r[1] = path[2 * idx + 1]; r[2] = 0.0; r[3] = vdes; r[4] = orient[idx];
+}
 __device__ __forceinline__ void ref_window_rows(int i, int N, int Tlen, const double* path, const double* orient, double vdes,
                                                 const double* x_now, double* xref /* [N+1][5] */) {
-  // desired_command_and_trajectory (optimizer.py:657-702, quirk Q8)
   for (int j = 0; j < 5; ++j) xref[j] = x_now[j];
-  for (int k = 0; k < N; ++k) {
-    const int idx = (i >= Tlen - N) ? (k + (Tlen - N)) : (i + k + 1);
-    double* r = xref + 5 * (k + 1);
-    r[0] = path[2 * idx]; r[1] = path[2 * idx + 1]; r[2] = 0.0; r[3] = vdes; r[4] = orient[idx];
-  }
+  for (int k = 0; k < N; ++k) ref_window_row(i, k, N, Tlen, path, orient, vdes, xref + 5 * (k + 1));
 }
 
-template <typename T, int LANES, bool SMEM_WS>
-__global__ void __launch_bounds__(32, 1) mpc_closed_loop_kernel(const LoopArgs<T> a) {
+// The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631) for one ego per warp, no host
+// round trip between MPC steps: solve, record u_0, plant step + warm-start shift, next reference window.
+template <typename T, int WPC>
+__global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const LoopArgs<T> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
-  const int tile = blockIdx.x;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
-  const Layout L(N);
-  const int base = tile * LANES;
-  const int nvalid = min(LANES, a.B - base);
-  const bool valid = lane < nvalid;
-  const int b = base + (valid ? lane : 0);
-  T* slab_s = reinterpret_cast<T*>(smem_raw);
-  T* slab_g = a.slab ? a.slab + (size_t)tile * L.words * LANES : nullptr;
-  T* wsbase = SMEM_WS ? slab_s : slab_g;
-  double* stage = SMEM_WS ? reinterpret_cast<double*>(slab_s + (size_t)L.o_K * LANES) : reinterpret_cast<double*>(smem_raw);
-  const int nx = 5 * (N + 1), nu = 2 * N;
-  double* my_xref = stage + (size_t)(lane < LANES ? lane : 0) * nx;
-  double* my_X = stage + (size_t)LANES * nx + (size_t)(lane < LANES ? lane : 0) * nx;
-  double* my_U = stage + (size_t)2 * LANES * nx + (size_t)(lane < LANES ? lane : 0) * nu;
-
-  Ws<T, LANES> ws{wsbase + (lane < LANES ? lane : 0)};
+  const WLayout L(N);
+  const Smem<T, WPC> sm(smem_raw, N, L.words);
+  const int nu = sm.nu;
+  const int b = blockIdx.x * WPC + wid;
+  if (b >= a.B) return;                                   // whole warp leaves; no CTA-wide barrier below
+  double* my_xref = sm.xref(wid);
+  double* my_X = sm.X(wid);
+  double* my_U = sm.U(wid);
+  const WarpCtx w;
   T obs[6];
-  Solver<T, LANES> S(a.P, ws, obs);
+  WarpSolver<T> S(a.P, sm.slab(wid), obs, w);
   ProbState<T> st;
   double x[5];
-  if (valid) {
-    for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
-    // first parameter block and warm start: the initial state tiled, controls zero (optimizer.py:578-583, quirk Q4)
-    for (int k = 0; k <= N; ++k)
-      for (int j = 0; j < 5; ++j) { my_xref[5 * k + j] = x[j]; my_X[5 * k + j] = x[j]; }
-    for (int k = 0; k < nu; ++k) my_U[k] = 0.0;
-  }
+  for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
+  // first parameter block and warm start: the initial state tiled, controls zero (optimizer.py:578-583, quirk Q4)
+  for (int k = lane; k <= N; k += 32)
+    for (int j = 0; j < 5; ++j) { my_xref[5 * k + j] = x[j]; my_X[5 * k + j] = x[j]; }
+  for (int k = lane; k < nu; k += 32) my_U[k] = 0.0;
+  __syncwarp();
   for (int i = 0; i < a.Tlen; ++i) {
-    if (valid) {
-      if (a.traj) for (int j = 0; j < 5; ++j) a.traj[((size_t)b * a.Tlen + i) * 5 + j] = x[j];   // quirk Q12
-      S.load(my_xref, my_X, my_U, a.obstacle, obs);
-    }
-    __syncwarp();
-    if (valid) S.init(st); else { st.done = 1; }
-    for (int it = 0; it < a.P.max_iter; ++it) {
-      if (__all_sync(0xffffffffu, st.done)) break;
-      if (!st.done) S.iterate(st);
-    }
-    __syncwarp();
-    if (valid) {
-      // the solve clobbered the aliased staging: rebuild this step's window, then write the solution over it
-      if (i == 0) { for (int k = 0; k <= N; ++k) for (int j = 0; j < 5; ++j) my_xref[5 * k + j] = x[j]; }
-      else ref_window_rows(i - 1, N, a.Tlen, a.path, a.orient, a.desired_velocity, x, my_xref);
-      S.store(my_xref, my_X, my_U);
-      const double u0 = my_U[0], u1 = my_U[1];
+    if (lane == 0 && a.traj) for (int j = 0; j < 5; ++j) a.traj[((size_t)b * a.Tlen + i) * 5 + j] = x[j];   // quirk Q12
+    S.load(my_xref, my_X, my_U, a.obstacle, obs);
+    S.init(st);
+    for (int it = 0; it < a.P.max_iter && !st.done; ++it) S.iterate(st);
+    S.store(my_xref, my_X, my_U);
+    const double u0 = my_U[0], u1 = my_U[1];
+    if (lane == 0) {
       if (a.ctrl) { a.ctrl[((size_t)b * a.Tlen + i) * 2] = u0; a.ctrl[((size_t)b * a.Tlen + i) * 2 + 1] = u1; }
       if (a.status) a.status[(size_t)b * a.Tlen + i] = st.status;
       if (a.iters) a.iters[(size_t)b * a.Tlen + i] = st.iters;
-      plant_euler(x, u0, u1, a.dt, a.l_wb);
-      // shift the warm start one stage, repeating the last (optimizer.py:652-653)
-      for (int k = 0; k < N - 1; ++k) { my_U[2 * k] = my_U[2 * k + 2]; my_U[2 * k + 1] = my_U[2 * k + 3]; }
-      for (int k = 0; k < N; ++k) for (int j = 0; j < 5; ++j) my_X[5 * k + j] = my_X[5 * (k + 1) + j];
-      // next window from the new state (optimizer.py:628)
-      ref_window_rows(i, N, a.Tlen, a.path, a.orient, a.desired_velocity, x, my_xref);
     }
+    plant_euler(x, u0, u1, a.dt, a.l_wb);
+    __syncwarp();
+    // shift the warm start one stage, repeating the last (optimizer.py:652-653); lane-strided with a register hop
+    for (int k0 = 0; k0 < N; k0 += 32) {
+      const int k = k0 + lane;
+      double nxt[7];
+      if (k < N) {
+        const int ks = (k + 1 < N) ? k + 1 : N - 1;
+        nxt[5] = my_U[2 * ks]; nxt[6] = my_U[2 * ks + 1];
+        for (int j = 0; j < 5; ++j) nxt[j] = my_X[5 * (k + 1) + j];
+      }
+      __syncwarp();
+      if (k < N) {
+        my_U[2 * k] = nxt[5]; my_U[2 * k + 1] = nxt[6];
+        for (int j = 0; j < 5; ++j) my_X[5 * k + j] = nxt[j];
+      }
+      __syncwarp();
+    }
+    // next window from the new state (optimizer.py:628)
+    if (lane == 0) for (int j = 0; j < 5; ++j) my_xref[j] = x[j];
+    for (int k = lane; k < N; k += 32) ref_window_row(i, k, N, a.Tlen, a.path, a.orient, a.desired_velocity, my_xref + 5 * (k + 1));
     __syncwarp();
   }
 }
@@ -339,11 +341,10 @@ __global__ void build_ref_window_kernel(int i, int Tlen, const double* path, con
 // ===================================================================================================== handle
 struct mpcb200_handle {
   mpcb200_config cfg;
-  int lanes;            // problems per CTA
-  bool smem_ws;         // slab in shared memory
+  int wpc;              // warps (= problems) per CTA
   size_t smem_bytes;
-  int words;
-  void* slab;           // global slab image (stepwise mode or global-workspace mode)
+  int words;            // slab words per problem
+  void* slab;           // global slab image [max_batch][words] (stepwise mode), allocated on first use
   void* state;
   void* obs_shift;
   size_t elem;          // sizeof(T)
@@ -354,7 +355,6 @@ struct mpcb200_handle {
   // host-path staging
   double *d_xref, *d_X, *d_U;
   int *d_status, *d_iters;
-  double *h_pin;
   std::string err;
 };
 
@@ -368,42 +368,45 @@ static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
 
-template <typename T, int LANES, bool SMEM_WS>
+template <typename T, int WPC>
 static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s) {
-  const int tiles = (a.B + LANES - 1) / LANES;
-  cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<T, LANES, SMEM_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  const int ctas = (a.B + WPC - 1) / WPC;
+  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) return e;
-  mpc_solve_kernel<T, LANES, SMEM_WS><<<tiles, 32, h->smem_bytes, s>>>(a);
+  mpc_warp_solve_kernel<T, WPC><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
-template <typename T, int LANES, bool SMEM_WS>
+template <typename T, int WPC>
 static cudaError_t launch_loop(mpcb200_handle* h, const LoopArgs<T>& a, cudaStream_t s) {
-  const int tiles = (a.B + LANES - 1) / LANES;
-  cudaError_t e = cudaFuncSetAttribute(mpc_closed_loop_kernel<T, LANES, SMEM_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  const int ctas = (a.B + WPC - 1) / WPC;
+  cudaError_t e = cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) return e;
-  mpc_closed_loop_kernel<T, LANES, SMEM_WS><<<tiles, 32, h->smem_bytes, s>>>(a);
+  mpc_warp_closed_loop_kernel<T, WPC><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s) {
-  if (h->smem_ws) {
-    if (h->lanes == 32) return launch_solve<T, 32, true>(h, a, s);
-    if (h->lanes == 16) return launch_solve<T, 16, true>(h, a, s);
-    return launch_solve<T, 8, true>(h, a, s);
-  }
-  return launch_solve<T, 32, false>(h, a, s);
+  if (h->wpc == 4) return launch_solve<T, 4>(h, a, s);
+  if (h->wpc == 2) return launch_solve<T, 2>(h, a, s);
+  return launch_solve<T, 1>(h, a, s);
 }
 template <typename T>
 static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t s) {
-  if (h->smem_ws) {
-    if (h->lanes == 32) return launch_loop<T, 32, true>(h, a, s);
-    if (h->lanes == 16) return launch_loop<T, 16, true>(h, a, s);
-    return launch_loop<T, 8, true>(h, a, s);
-  }
-  return launch_loop<T, 32, false>(h, a, s);
+  if (h->wpc == 4) return launch_loop<T, 4>(h, a, s);
+  if (h->wpc == 2) return launch_loop<T, 2>(h, a, s);
+  return launch_loop<T, 1>(h, a, s);
+}
+
+static int ensure_stepwise_scratch(mpcb200_handle* h) {
+  if (h->slab) return 0;
+  const size_t mb = (size_t)h->cfg.max_batch;
+  CK(cudaMalloc(&h->slab, mb * h->words * h->elem));
+  CK(cudaMalloc(&h->state, mb * sizeof(ProbState<double>)));
+  CK(cudaMalloc(&h->obs_shift, mb * 6 * h->elem));
+  return 0;
 }
 
 template <typename T>
@@ -411,6 +414,7 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
                     int B, cudaStream_t s) {
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  if (mode != MODE_ONESHOT) { int rc = ensure_stepwise_scratch(h); if (rc) return rc; }
   SolveArgs<T> a;
   a.P = params_from_config<T>(h->cfg);
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
@@ -418,7 +422,7 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   a.slab = (T*)h->slab; a.state = (ProbState<T>*)h->state; a.obs_shift = (T*)h->obs_shift;
   a.B = B; a.mode = mode; a.n_iter = n_iter;
   cudaError_t e = dispatch_solve<T>(h, a, s);
-  if (e != cudaSuccess) return fail(h, "mpc_solve_kernel launch", e);
+  if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel launch", e);
   return 0;
 }
 
@@ -446,31 +450,21 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   if (!h) { g_create_err = "out of host memory"; return -4; }
   h->cfg = *cfg;
   h->launches = 0; h->slab = h->state = h->obs_shift = nullptr;
-  h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
+  h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr;
   h->sw_xref = nullptr; h->sw_B = 0;
-  const Layout L(cfg->N);
+  const WLayout L(cfg->N);
   h->words = L.words;
   h->elem = cfg->precision == MPCB200_F64 ? 8 : 4;
   const size_t smem_max = prop.sharedMemPerBlockOptin;   // 227 KB on B200
   const size_t reserve = 1024;
-  h->smem_ws = false; h->lanes = 32;
-  for (int lanes : {32, 16, 8}) {
-    const size_t need = (size_t)L.words * lanes * h->elem;
-    if (need + reserve <= smem_max) { h->smem_ws = true; h->lanes = lanes; h->smem_bytes = need; break; }
+  h->wpc = 0;
+  int wpc_pref = 2;
+  if (const char* ev = getenv("MPCB200_WPC")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) wpc_pref = v; }   // tuning knob
+  for (int wpc : {wpc_pref, 2, 1}) {
+    const size_t need = smem_bytes_for(cfg->N, L.words, h->elem, wpc);
+    if (need + reserve <= smem_max) { h->wpc = wpc; h->smem_bytes = need; break; }
   }
-  if (!h->smem_ws) {
-    h->lanes = 32;
-    h->smem_bytes = (size_t)32 * (12 * cfg->N + 10) * sizeof(double);   // float64 staging only
-    if (h->smem_bytes + reserve > smem_max) { g_create_err = "horizon too long for the staging buffer"; delete h; return -2; }
-  }
-  const size_t tiles = ((size_t)cfg->max_batch + h->lanes - 1) / h->lanes;
-  if (cudaMalloc(&h->slab, tiles * L.words * h->lanes * h->elem) != cudaSuccess ||
-      cudaMalloc(&h->state, (size_t)cfg->max_batch * sizeof(ProbState<double>)) != cudaSuccess ||
-      cudaMalloc(&h->obs_shift, (size_t)cfg->max_batch * 6 * h->elem) != cudaSuccess) {
-    fail(nullptr, "cudaMalloc of solver scratch", cudaGetLastError());
-    mpcb200_destroy(h);
-    return -4;
-  }
+  if (!h->wpc) { g_create_err = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2; }
   *out = h;
   return 0;
 }
@@ -479,7 +473,6 @@ void mpcb200_destroy(mpcb200_handle* h) {
   if (!h) return;
   cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift);
   cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);
-  if (h->h_pin) cudaFreeHost(h->h_pin);
   delete h;
 }
 
@@ -551,14 +544,14 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
     a.P = params_from_config<double>(h->cfg);
     for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
     a.path = d_path; a.orient = d_orientation; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
-    a.slab = (double*)h->slab; a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
+    a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
     e = dispatch_loop<double>(h, a, (cudaStream_t)stream);
   } else {
     LoopArgs<float> a;
     a.P = params_from_config<float>(h->cfg);
     for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
     a.path = d_path; a.orient = d_orientation; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
-    a.slab = (float*)h->slab; a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
+    a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
     e = dispatch_loop<float>(h, a, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return fail(h, "mpc_closed_loop_kernel launch", e);
@@ -591,6 +584,6 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, dou
 
 int64_t mpcb200_launch_count(const mpcb200_handle* h) { return h ? h->launches : 0; }
 int32_t mpcb200_workspace_words(const mpcb200_handle* h) { return h ? h->words : 0; }
-int32_t mpcb200_slab_in_smem(const mpcb200_handle* h) { return h ? (h->smem_ws ? h->lanes : 0) : 0; }
+int32_t mpcb200_slab_in_smem(const mpcb200_handle* h) { return h ? h->wpc : 0; }
 
 }  // extern "C"

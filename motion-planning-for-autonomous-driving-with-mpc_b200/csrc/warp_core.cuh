@@ -1,0 +1,749 @@
+// warp_core.cuh -- warp-cooperative nonlinear-MPC solver core: ONE WARP PER EGO INSTANCE (one NLP).
+//
+// Solves the NLP the reference hands to IPOPT each MPC step (/root/reference/MPC_Planner/optimizer.py:513-560;
+// constraints :373-411, bounds :413-491, cost :493-511) with the same primal-dual interior-point / SQP-type iteration
+// as sqp_core.cuh (same formulas, same globalisation), re-mapped onto 32 lanes:
+//
+//   * phases that are independent per stage -- linearisation of the Euler multiple-shooting defects
+//     (optimizer.py:380-382) and the 10 inequality rows per stage into the stage KKT block, step-length limits,
+//     line-search merit terms, the step commit -- run LANE = STAGE (k = lane, lane+32, ...), with warp reductions
+//     (REDUX / shuffle butterflies) for the merit, the fraction-to-the-boundary limits and the convergence test;
+//   * the backward Riccati sweep (block LDL^T of the block-tridiagonal KKT matrix in stage order
+//     u_0, x_1, u_1, x_2, ...) runs LANE = MATRIX ENTRY: the cost-to-go is the 5x6 augmented block [P | p]
+//     (lane 6i+j holds entry (i,j), only the upper triangle of P is ever a shuffle source, so P stays exactly
+//     symmetric); one stage = 15 shuffles in two rounds, ~25 FMAs, one reciprocal of the 2x2 control block
+//     determinant.  A_k = I + dt*df/dx has 6 off-identity entries and B = dt*[e_delta e_v] is constant, so the
+//     products P*A and A^T*M touch at most 3-5 sources per entry;
+//   * the forward sweep runs LANE = STATE COMPONENT (5 lanes + 5 broadcast shuffles per stage).
+//
+// The per-problem KKT slab (iterate, reference, multipliers, slacks, trig cache, stage KKT blocks, gains, step) is
+// 94N+21 words and lives in shared memory; stage records have an odd stride so LANE = STAGE accesses are
+// bank-conflict free and LANE = ENTRY accesses of one record are contiguous.
+//
+// New code: the reference contains no solver of its own (it calls casadi/IPOPT).  The same source compiles for the
+// device (nvcc) and, through the fiber emulator in warp_ctx.cuh, for the host-side algorithm tests (tests/host_sim).
+#pragma once
+#include "sqp_core.cuh"
+#include "warp_ctx.cuh"
+
+namespace mpcb200 {
+
+// ------------------------------------------------------------------ slab layout (words of T per problem)
+// stage record k = 0..N-1  (terms of u_k, of the dynamics x_k -> x_{k+1} and of x_{k+1})
+enum : int {
+  R_U = 0,      // 2  controls u_k
+  R_V = 2,      // 11 multipliers of the inequality rows (slot order of sqp_core.cuh: V_DD_LO ...)
+  R_S = 13,     // 3  obstacle slacks
+  R_CP = 16,    // 2  reference position increment rho_k - rho_{k+1} (from float64)
+  R_E = 18,     // 6  off-identity entries of A_k: e03 e04 e13 e14 e42 e43
+  R_D = 24,     // 5  dynamics defect d_k
+  R_ZERO = 29,  // 1  constant 0 (target of structurally-zero coefficient indices)
+  R_ONE = 30,   // 1  constant 1
+  R_H = 31,     // 8  Hessian of the x_{k+1} terms: h00 h01 h04 h11 h14 h44 h22 h33
+  R_GX = 39,    // 5  gradient of the x_{k+1} terms (barrier gradient at the current mu)
+  R_RU = 44,    // 4  Ru0 Ru1 ru0 ru1 (control Hessian diagonal / gradient incl. barrier terms)
+  R_LC = 48,    // 5  multiplier-weighted gradient of the x_{k+1} terms (adjoint recursion, exact Hessian)
+  R_KK = 53,    // 12 gains: K0[0..4] k0 K1[0..4] k1
+  R_DX = 65,    // 5  step dx_{k+1}
+  R_DU = 70,    // 2  step du_k
+  REC_STRIDE = 73
+};
+// state record k = 0..N
+enum : int {
+  S_XR = 0,     // 5 rho_k (reference row paired with stage k, frame shifted to the pinned position)
+  S_XT = 5,     // 5 deviation state xt_k = x_k - rho_k
+  S_TR = 10,    // 3 sin(psi_k) cos(psi_k) tan(delta_k)
+  S_XTT = 13,   // 5 trial deviation state
+  S_TRT = 18,   // 3 trig of the trial state
+  ST_STRIDE = 21
+};
+enum : int { E03 = 0, E04, E13, E14, E42, E43 };
+enum : int { H00 = 0, H01, H04, H11, H14, H44, H22, H33 };
+
+struct WLayout {
+  int N, o_state, o_rec, words;
+  MPC_HD explicit WLayout(int N_) : N(N_) {
+    o_state = 0;
+    o_rec = ST_STRIDE * (N + 1);
+    words = (o_rec + REC_STRIDE * N + 3) & ~3;     // multiple of 4 words: 16-byte granularity for bulk copies
+  }
+};
+
+// record offset of E[l][m] = (A_k - I)[l][m], or the ZERO slot
+MPC_HD int e_off(int l, int m) {
+  if (l == 0 && m == 3) return R_E + E03;
+  if (l == 0 && m == 4) return R_E + E04;
+  if (l == 1 && m == 3) return R_E + E13;
+  if (l == 1 && m == 4) return R_E + E14;
+  if (l == 4 && m == 2) return R_E + E42;
+  if (l == 4 && m == 3) return R_E + E43;
+  return R_ZERO;
+}
+
+// per-lane index tables of the serial sweeps (registers; computed once per kernel)
+struct LaneTab {
+  int i, j;        // entry of the 5x6 augmented block [P | p] this lane holds
+  int own;         // 1 for the affine column j == 5
+  int hidx;        // record offset of the x_{k+1} Hessian / gradient term this lane accumulates
+  int exw;         // exact-Hessian addition: 0 none, 1 (4,4), 2 (3,4), 3 (2,2), 4 (2,3)
+  int c[5];        // record offsets of Atilde[t][j], t = 0..4   (M = [P|p] * Atilde)
+  int s1[5];       // source lanes of P[i][t] (upper-triangle storage)
+  int e[3];        // record offsets of E[l_t][i]                  (Pn = A^T M - H^T G^-1 H)
+  int s2[3];       // source lanes of M[l_t][j]
+  int s_m2j, s_m3j, s_m2i, s_m3i;
+  int fc[5], fc0;  // forward sweep, lanes 0..4: coefficients of row `lane` and of the constant term
+  int fscale;      // 1: rows 2,3 (acc is du, scaled by dt), 0: rows 0,1,4
+  MPC_HD explicit LaneTab(int lane) {
+    const int l = lane < 30 ? lane : 0;
+    i = l / 6; j = l % 6;
+    own = (j == 5) ? 1 : 0;
+    hidx = R_ZERO; exw = 0;
+    if (j == 5) hidx = R_GX + i;
+    else if (i <= j) {
+      if (i == 0 && j == 0) hidx = R_H + H00;
+      if (i == 0 && j == 1) hidx = R_H + H01;
+      if (i == 0 && j == 4) hidx = R_H + H04;
+      if (i == 1 && j == 1) hidx = R_H + H11;
+      if (i == 1 && j == 4) hidx = R_H + H14;
+      if (i == 4 && j == 4) { hidx = R_H + H44; exw = 1; }
+      if (i == 2 && j == 2) { hidx = R_H + H22; exw = 3; }
+      if (i == 3 && j == 3) hidx = R_H + H33;
+      if (i == 3 && j == 4) exw = 2;
+      if (i == 2 && j == 3) exw = 4;
+    }
+    for (int t = 0; t < 5; ++t) {
+      c[t] = (j == 5) ? (R_D + t) : ((t == j) ? R_ONE : e_off(t, j));
+      s1[t] = (i <= t) ? (6 * i + t) : (6 * t + i);
+    }
+    int src[3] = {0, 0, 0}, n = 0;
+    for (int t = 0; t < 3; ++t) e[t] = R_ZERO;
+    for (int ll = 0; ll < 5; ++ll) {
+      if (e_off(ll, i) != R_ZERO && n < 3) { e[n] = e_off(ll, i); src[n] = ll; ++n; }
+    }
+    for (int t = 0; t < 3; ++t) s2[t] = 6 * src[t] + j;
+    s_m2j = 12 + j; s_m3j = 18 + j; s_m2i = 12 + i; s_m3i = 18 + i;
+    const int r = lane < 5 ? lane : 0;
+    fscale = (r == 2 || r == 3) ? 1 : 0;
+    for (int t = 0; t < 5; ++t) fc[t] = (r == 2) ? (R_KK + t) : (r == 3) ? (R_KK + 6 + t) : e_off(r, t);
+    fc0 = (r == 2) ? (R_KK + 5) : (r == 3) ? (R_KK + 11) : R_ZERO;
+  }
+};
+
+template <typename T>
+struct WarpSolver {
+  const ParamsT<T>& P;
+  const WLayout L;
+  T* sl;             // this problem's slab
+  const T* obs;      // obstacle circle centres (centre, front, rear) in the problem's shifted frame
+  const WarpCtx& w;
+  const int lane;
+  const LaneTab tb;
+
+  MPC_HD WarpSolver(const ParamsT<T>& P_, T* slab, const T* obs_, const WarpCtx& w_)
+      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()) {}
+
+  MPC_HD T& sx(int k, int f) const { return sl[L.o_state + ST_STRIDE * k + f]; }
+  MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + REC_STRIDE * k + f]; }
+  MPC_HD T xa(int k, int j) const { return sx(k, S_XT + j) + sx(k, S_XR + j); }
+
+  struct Trig { T sn, cs, tn; };
+  MPC_HD Trig trig_of(T psi, T delta) const { Trig t; m_sincos(psi, &t.sn, &t.cs); t.tn = m_tan(delta); return t; }
+
+  // obstacle row j at (sx, sy, psi): distance + gradient (optimizer.py:384-403; distinct rows only, quirk Q6)
+  MPC_HD void obst(int j, T px, T py, T sn, T cs, T& h, T& gx, T& gy, T& gp) const {
+    const T sg = (j == 0) ? T(0) : (j == 1 ? T(1) : T(-1));
+    const T o = sg * P.ego_off;
+    const T dx = px + o * cs - obs[2 * j], dy = py + o * sn - obs[2 * j + 1];
+    h = m_sqrt(dx * dx + dy * dy);
+    const T ih = T(1) / m_max(h, T(1e-12));
+    gx = dx * ih; gy = dy * ih;
+    gp = o * (gy * cs - gx * sn);
+  }
+
+  // defect of stage k: d = xt_k - xt_{k+1} + dt*f(x_k,u_k) + (rho_k - rho_{k+1})      (optimizer.py:380-382, Euler)
+  MPC_HD void defect(int k, const T* x0d, const T* x1d, T v, const Trig& t, T u0, T u1, T* d) const {
+    const T dt = P.dt;
+    d[0] = (x0d[0] - x1d[0]) + dt * v * t.cs + rc(k, R_CP);
+    d[1] = (x0d[1] - x1d[1]) + dt * v * t.sn + rc(k, R_CP + 1);
+    d[2] = (x0d[2] - x1d[2]) + dt * u0 + (sx(k, S_XR + 2) - sx(k + 1, S_XR + 2));
+    d[3] = (x0d[3] - x1d[3]) + dt * u1 + (sx(k, S_XR + 3) - sx(k + 1, S_XR + 3));
+    d[4] = (x0d[4] - x1d[4]) + dt * v * t.tn / P.l_wb + (sx(k, S_XR + 4) - sx(k + 1, S_XR + 4));
+  }
+
+  // ---------------------------------------------------------------- problem I/O (float64 row-major arrays of ONE problem)
+  // xref [N+1][5] (row 0 = pinned state), Xin [N+1][5], Uin [N][2].  Differences are formed in float64, then rounded.
+  MPC_HD void load(const double* xref, const double* Xin, const double* Uin, const double* obstacle_abs, T* obs_out) const {
+    const int N = P.N;
+    const double ox = xref[0], oy = xref[1];
+    for (int j = 0; j < 3; ++j) { obs_out[2 * j] = (T)(obstacle_abs[2 * j] - ox); obs_out[2 * j + 1] = (T)(obstacle_abs[2 * j + 1] - oy); }
+    for (int k = lane; k <= N; k += 32) {
+      const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
+      const double* xin = (k == 0) ? xref : (Xin + 5 * k);           // stage 0 is pinned to X_ref[:,0]
+      sx(k, S_XR + 0) = (T)(rho[0] - ox); sx(k, S_XR + 1) = (T)(rho[1] - oy);
+      sx(k, S_XR + 2) = (T)rho[2]; sx(k, S_XR + 3) = (T)rho[3]; sx(k, S_XR + 4) = (T)rho[4];
+      for (int j = 0; j < 5; ++j) sx(k, S_XT + j) = (T)(xin[j] - rho[j]);
+      if (k < N) {
+        const double* rho1 = xref + 5 * ((k + 2 < N) ? (k + 2) : N);
+        rc(k, R_CP) = (T)(rho[0] - rho1[0]); rc(k, R_CP + 1) = (T)(rho[1] - rho1[1]);
+        rc(k, R_U) = (T)Uin[2 * k]; rc(k, R_U + 1) = (T)Uin[2 * k + 1];
+        rc(k, R_ZERO) = T(0); rc(k, R_ONE) = T(1);
+      }
+    }
+    w.sync();
+  }
+  MPC_HD void store(const double* xref, double* Xout, double* Uout) const {
+    const int N = P.N;
+    w.sync();
+    for (int k = lane; k <= N; k += 32) {
+      const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
+      for (int j = 0; j < 5; ++j) Xout[5 * k + j] = (k == 0) ? xref[j] : ((double)sx(k, S_XT + j) + rho[j]);
+      if (k < N) { Uout[2 * k] = (double)rc(k, R_U); Uout[2 * k + 1] = (double)rc(k, R_U + 1); }
+    }
+    w.sync();
+  }
+
+  // ---------------------------------------------------------------- initialisation (lane = stage)
+  // Pushes the start point strictly inside the bounds and puts slacks / multipliers on the central path; fills the
+  // trig cache.  Every lane ends with the same (uniform) ProbState.
+  MPC_HD void init(ProbState<T>& st) const {
+    const int N = P.N;
+    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.kkt = T(0);
+    st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
+    const T de0 = xa(0, 2), v0 = xa(0, 3);
+    const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
+    bool bad = false;
+    // friction row (optimizer.py:378, 424-425): |a0^2 + s0| <= a_max is the box |a0| <= sqrt(a_max - s0) when |s0| < a_max
+    if (!(s0 < P.a_max) || !(s0 > -P.a_max)) bad = true;
+    const T amax0 = m_sqrt(m_max(P.a_max - s0, T(1e-12)));
+    st.a0_hi = m_min(amax0, P.a_max);
+    st.a0_lo = -amax0;
+    if (de0 < P.de_min || de0 > P.de_max || v0 < P.v_min || v0 > P.v_max) bad = true;
+    {
+      T sn, cs; m_sincos(xa(0, 4), &sn, &cs);
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, xa(0, 0), xa(0, 1), sn, cs, h, gx, gy, gp);
+        if (h < P.r_sum) bad = true;
+      }
+    }
+    if (bad) { st.status = ST_INFEASIBLE_X0; st.done = 1; }
+    const T kp = P.bound_push;
+    if (lane == 0) {
+      const Trig t = trig_of(xa(0, 4), xa(0, 2));
+      sx(0, S_TR) = t.sn; sx(0, S_TR + 1) = t.cs; sx(0, S_TR + 2) = t.tn;
+      sx(0, S_TRT) = t.sn; sx(0, S_TRT + 1) = t.cs; sx(0, S_TRT + 2) = t.tn;
+      for (int j = 0; j < 5; ++j) sx(0, S_XTT + j) = sx(0, S_XT + j);
+    }
+    for (int k = lane; k < N; k += 32) {
+      const T mu = st.mu;
+      const T pdd = m_min(kp, kp * (P.dd_max - P.dd_min));
+      T dd = m_min(m_max(rc(k, R_U), P.dd_min + pdd), P.dd_max - pdd);
+      const T ahi = (k == 0) ? st.a0_hi : P.a_max;
+      T a = rc(k, R_U + 1);
+      if (k == 0) {
+        const T pa = m_min(kp * m_max(T(1), ahi), kp * (ahi - st.a0_lo));
+        a = m_min(m_max(a, st.a0_lo + pa), ahi - pa);
+      } else {
+        a = m_min(a, ahi - kp * m_max(T(1), m_abs(ahi)));
+      }
+      rc(k, R_U) = dd; rc(k, R_U + 1) = a;
+      const T pde = m_min(kp * m_max(T(1), m_abs(P.de_max)), kp * (P.de_max - P.de_min));
+      const T pv = m_min(kp * m_max(T(1), m_abs(P.v_max)), kp * (P.v_max - P.v_min));
+      const T de = m_min(m_max(xa(k + 1, 2), P.de_min + pde), P.de_max - pde);
+      const T vv = m_min(m_max(xa(k + 1, 3), P.v_min + pv), P.v_max - pv);
+      sx(k + 1, S_XT + 2) = de - sx(k + 1, S_XR + 2);
+      sx(k + 1, S_XT + 3) = vv - sx(k + 1, S_XR + 3);
+      rc(k, R_V + V_DD_LO) = mu / (dd - P.dd_min);
+      rc(k, R_V + V_DD_HI) = mu / (P.dd_max - dd);
+      rc(k, R_V + V_A_HI) = mu / (ahi - a);
+      rc(k, R_V + V_A_LO) = (k == 0) ? mu / (a - st.a0_lo) : T(0);
+      rc(k, R_V + V_DE_LO) = mu / (de - P.de_min);
+      rc(k, R_V + V_DE_HI) = mu / (P.de_max - de);
+      rc(k, R_V + V_V_LO) = mu / (vv - P.v_min);
+      rc(k, R_V + V_V_HI) = mu / (P.v_max - vv);
+      const Trig t = trig_of(xa(k + 1, 4), xa(k + 1, 2));
+      sx(k + 1, S_TR) = t.sn; sx(k + 1, S_TR + 1) = t.cs; sx(k + 1, S_TR + 2) = t.tn;
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, xa(k + 1, 0), xa(k + 1, 1), t.sn, t.cs, h, gx, gy, gp);
+        const T c = h - P.r_sum;
+        const T s = m_max(c, kp * m_max(T(1), P.r_sum));
+        rc(k, R_S + j) = s;
+        rc(k, R_V + V_OB0 + j) = mu / s;
+      }
+      for (int j = 0; j < 5; ++j) rc(k, R_DX + j) = T(0);
+      rc(k, R_DU) = T(0); rc(k, R_DU + 1) = T(0);
+    }
+    w.sync();
+  }
+
+  // ---------------------------------------------------------------- phase A: stage KKT blocks (lane = stage)
+  MPC_HD void linearize(const ProbState<T>& st) const {
+    const int N = P.N;
+    const T dt = P.dt, mu = st.mu;
+    for (int k = lane; k < N; k += 32) {
+      T x0d[5], x1d[5], x1a[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { x0d[j] = sx(k, S_XT + j); x1d[j] = sx(k + 1, S_XT + j); x1a[j] = x1d[j] + sx(k + 1, S_XR + j); }
+      const T v = x0d[3] + sx(k, S_XR + 3);
+      Trig t0, t1;
+      t0.sn = sx(k, S_TR); t0.cs = sx(k, S_TR + 1); t0.tn = sx(k, S_TR + 2);
+      t1.sn = sx(k + 1, S_TR); t1.cs = sx(k + 1, S_TR + 1);
+      const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
+      // dynamics: A_k = I + dt*df/dx (configuration.py:364-368), defect
+      const T sec2 = T(1) + t0.tn * t0.tn;
+      rc(k, R_E + E03) = dt * t0.cs; rc(k, R_E + E04) = -dt * v * t0.sn;
+      rc(k, R_E + E13) = dt * t0.sn; rc(k, R_E + E14) = dt * v * t0.cs;
+      rc(k, R_E + E42) = dt * v * sec2 / P.l_wb; rc(k, R_E + E43) = dt * t0.tn / P.l_wb;
+      T d[5];
+      defect(k, x0d, x1d, v, t0, u0, u1, d);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) rc(k, R_D + j) = d[j];
+      // x_{k+1} terms: cost (stages 1..N-1 only, quirk Q1), box barriers, obstacle barriers
+      T hd[5], g[5], lc[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { hd[j] = T(0); g[j] = T(0); lc[j] = T(0); }
+      if (k + 1 <= N - 1) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { const T gq = T(2) * P.Q[j] * x1d[j]; hd[j] = T(2) * P.Q[j]; g[j] = gq; lc[j] = gq; }
+      }
+      {
+        const T slo = m_slack(x1a[2] - P.de_min), shi = m_slack(P.de_max - x1a[2]);
+        const T vlo = rc(k, R_V + V_DE_LO), vhi = rc(k, R_V + V_DE_HI);
+        hd[2] += vlo / slo + vhi / shi;
+        g[2] += -mu / slo + mu / shi;
+        lc[2] += -vlo + vhi;
+      }
+      {
+        const T slo = m_slack(x1a[3] - P.v_min), shi = m_slack(P.v_max - x1a[3]);
+        const T vlo = rc(k, R_V + V_V_LO), vhi = rc(k, R_V + V_V_HI);
+        hd[3] += vlo / slo + vhi / shi;
+        g[3] += -mu / slo + mu / shi;
+        lc[3] += -vlo + vhi;
+      }
+      T h01 = T(0), h04 = T(0), h14 = T(0);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, x1a[0], x1a[1], t1.sn, t1.cs, h, gx, gy, gp);
+        // slack reset s <- max(s, c(x)) (Nocedal & Wright 19.3)
+        T s = rc(k, R_S + j);
+        if (h - P.r_sum > s) { s = h - P.r_sum; rc(k, R_S + j) = s; }
+        const T nu = rc(k, R_V + V_OB0 + j);
+        const T wgt = nu / s, r = (h - P.r_sum) - s;
+        const T cg = -(mu / s - wgt * r);
+        hd[0] += wgt * gx * gx; h01 += wgt * gx * gy; h04 += wgt * gx * gp;
+        hd[1] += wgt * gy * gy; h14 += wgt * gy * gp; hd[4] += wgt * gp * gp;
+        g[0] += cg * gx; g[1] += cg * gy; g[4] += cg * gp;
+        lc[0] -= nu * gx; lc[1] -= nu * gy; lc[4] -= nu * gp;
+      }
+      rc(k, R_H + H00) = hd[0]; rc(k, R_H + H01) = h01; rc(k, R_H + H04) = h04; rc(k, R_H + H11) = hd[1];
+      rc(k, R_H + H14) = h14; rc(k, R_H + H44) = hd[4]; rc(k, R_H + H22) = hd[2]; rc(k, R_H + H33) = hd[3];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { rc(k, R_GX + j) = g[j]; rc(k, R_LC + j) = lc[j]; }
+      // control terms
+      {
+        const T slo = m_slack(u0 - P.dd_min), shi = m_slack(P.dd_max - u0);
+        T Ru0 = T(2) * P.R[0] + rc(k, R_V + V_DD_LO) / slo + rc(k, R_V + V_DD_HI) / shi;
+        T ru0 = T(2) * P.R[0] * u0 - mu / slo + mu / shi;
+        const T ahi = (k == 0) ? st.a0_hi : P.a_max;
+        const T sh = m_slack(ahi - u1);
+        T Ru1 = T(2) * P.R[1] + rc(k, R_V + V_A_HI) / sh;
+        T ru1 = T(2) * P.R[1] * u1 + mu / sh;
+        if (k == 0) {
+          const T sl_ = m_slack(u1 - st.a0_lo);
+          Ru1 += rc(k, R_V + V_A_LO) / sl_;
+          ru1 -= mu / sl_;
+        }
+        rc(k, R_RU) = Ru0; rc(k, R_RU + 1) = Ru1; rc(k, R_RU + 2) = ru0; rc(k, R_RU + 3) = ru1;
+      }
+    }
+    w.sync();
+  }
+
+  // ---------------------------------------------------------------- phase C: backward Riccati sweep (lane = entry of [P | p])
+  // Returns false (uniformly) if an exact-Hessian control block was not positive definite (caller retries with GN).
+  MPC_HD bool backward(int hess) const {
+    const int N = P.N;
+    const T dt = P.dt, dt2 = dt * dt;
+    T Pij = T(0);
+    T lam[5] = {T(0), T(0), T(0), T(0), T(0)};
+    const T ownf = (T)tb.own;
+    const T isj5 = ownf;
+    bool ok = true;
+    for (int k = N - 1; k >= 0; --k) {
+      const T* r = &rc(k, 0);
+      const T hterm = r[tb.hidx];
+      const T c0 = r[tb.c[0]], c1 = r[tb.c[1]], c2 = r[tb.c[2]], c3 = r[tb.c[3]], c4 = r[tb.c[4]];
+      const T e0 = r[tb.e[0]], e1 = r[tb.e[1]], e2 = r[tb.e[2]];
+      const T Ru0 = r[R_RU], Ru1 = r[R_RU + 1], ru0 = r[R_RU + 2], ru1 = r[R_RU + 3];
+      Pij += hterm;                                   // x_{k+1} terms
+      // round 1: control block + M = [P|p] * Atilde
+      const T p22 = w.shfl(Pij, 14), p23 = w.shfl(Pij, 15), p33 = w.shfl(Pij, 21);
+      const T q0 = w.shfl(Pij, tb.s1[0]), q1 = w.shfl(Pij, tb.s1[1]), q2 = w.shfl(Pij, tb.s1[2]);
+      const T q3 = w.shfl(Pij, tb.s1[3]), q4 = w.shfl(Pij, tb.s1[4]);
+      const T M = ownf * Pij + ((c0 * q0 + c1 * q1) + (c2 * q2 + c3 * q3) + c4 * q4);
+      const T G00 = Ru0 + dt2 * p22, G01 = dt2 * p23, G11 = Ru1 + dt2 * p33;
+      const T det = G00 * G11 - G01 * G01;
+      if (hess == HESS_EXACT) {
+        if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) { ok = false; break; }      // uniform across lanes
+      }
+      const T idet = T(1) / det;
+      const T I00 = G11 * idet, I01 = -G01 * idet, I11 = G00 * idet;
+      // round 2: H = B^T M (+ ru on the affine column), Pn = A^T M - H^T G^-1 H
+      const T m2j = w.shfl(M, tb.s_m2j), m3j = w.shfl(M, tb.s_m3j);
+      const T m2i = w.shfl(M, tb.s_m2i), m3i = w.shfl(M, tb.s_m3i);
+      const T r0 = w.shfl(M, tb.s2[0]), r1 = w.shfl(M, tb.s2[1]), r2 = w.shfl(M, tb.s2[2]);
+      const T H0j = dt * m2j + isj5 * ru0, H1j = dt * m3j + isj5 * ru1;
+      const T K0j = -(I00 * H0j + I01 * H1j), K1j = -(I01 * H0j + I11 * H1j);
+      const T H0i = dt * m2i, H1i = dt * m3i;
+      T Pn = (M + e0 * r0) + (e1 * r1 + e2 * r2) + (H0i * K0j + H1i * K1j);
+      if (lane < 6) { rc(k, R_KK + tb.j) = K0j; rc(k, R_KK + 6 + tb.j) = K1j; }
+      if (hess == HESS_EXACT) {
+        // adjoint multipliers lam_{k+1} (every lane keeps the 5-vector), then
+        // + dt * sum_i lam_{k+1,i} * hess f_i(x_k) on the (delta, v, psi) block of P_k
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) lam[jj] += r[R_LC + jj];
+        const T v = xa(k, 3);
+        const T sn = sx(k, S_TR), cs = sx(k, S_TR + 1), tn = sx(k, S_TR + 2);
+        const T sec2 = T(1) + tn * tn;
+        T ex = T(0);
+        if (tb.exw == 1) ex = dt * (-lam[0] * v * cs - lam[1] * v * sn);
+        if (tb.exw == 2) ex = dt * (-lam[0] * sn + lam[1] * cs);
+        if (tb.exw == 3) ex = dt * lam[4] * T(2) * v / P.l_wb * sec2 * tn;
+        if (tb.exw == 4) ex = dt * lam[4] * sec2 / P.l_wb;
+        Pn += ex;
+        const T f03 = r[R_E + E03], f04 = r[R_E + E04], f13 = r[R_E + E13], f14 = r[R_E + E14];
+        const T f42 = r[R_E + E42], f43 = r[R_E + E43];
+        const T l2 = lam[2] + f42 * lam[4];
+        const T l3 = lam[3] + f03 * lam[0] + f13 * lam[1] + f43 * lam[4];
+        const T l4 = lam[4] + f04 * lam[0] + f14 * lam[1];
+        lam[2] = l2; lam[3] = l3; lam[4] = l4;
+      }
+      Pij = Pn;
+    }
+    w.sync();
+    return ok;
+  }
+
+  // ---------------------------------------------------------------- phase D: forward sweep (lane = state component)
+  MPC_HD void forward_sweep() const {
+    const int N = P.N;
+    const T dt = P.dt;
+    const T scale = tb.fscale ? dt : T(1);
+    const int row = lane < 5 ? lane : 0;
+    T dx0 = T(0), dx1 = T(0), dx2 = T(0), dx3 = T(0), dx4 = T(0), mine = T(0);
+    for (int k = 0; k < N; ++k) {
+      const T* r = &rc(k, 0);
+      const T acc = r[tb.fc0] + ((r[tb.fc[0]] * dx0 + r[tb.fc[1]] * dx1) + (r[tb.fc[2]] * dx2 + r[tb.fc[3]] * dx3) + r[tb.fc[4]] * dx4);
+      const T nx = mine + scale * acc + r[R_D + row];
+      dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);
+      mine = nx;
+      if (lane < 5) rc(k, R_DX + lane) = nx;
+      if (lane == 2) rc(k, R_DU) = acc;
+      if (lane == 3) rc(k, R_DU + 1) = acc;
+    }
+    w.sync();
+  }
+
+  // ---------------------------------------------------------------- phase E: step-length limits, merit slope (lane = stage)
+  struct FwdOut { T a_p, a_d, dphi, c1, step_inf, mag; };
+
+  MPC_HD void row_limits(T s, T nu, T ds, T mu, T tau, FwdOut& o) const {
+    const T dnu = (mu - nu * s - nu * ds) / s;
+    if (ds < T(0)) o.a_p = m_min(o.a_p, -tau * s / ds);
+    if (dnu < T(0)) o.a_d = m_min(o.a_d, -tau * nu / dnu);
+    o.dphi += -mu * ds / s;
+  }
+
+  MPC_HD FwdOut forward_stats(const ProbState<T>& st) const {
+    const int N = P.N;
+    const T dt = P.dt, mu = st.mu;
+    const T tau = m_max(P.tau_min, T(1) - mu);
+    FwdOut o; o.a_p = T(1); o.a_d = T(1); o.dphi = T(0); o.c1 = T(0); o.step_inf = T(0); o.mag = T(0);
+    for (int k = lane; k < N; k += 32) {
+      T x0d[5], x1d[5], x1a[5], nx[5], d[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        x0d[j] = sx(k, S_XT + j); x1d[j] = sx(k + 1, S_XT + j); x1a[j] = x1d[j] + sx(k + 1, S_XR + j);
+        nx[j] = rc(k, R_DX + j); d[j] = rc(k, R_D + j);
+      }
+      const T v = x0d[3] + sx(k, S_XR + 3);
+      const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
+      const T du0 = rc(k, R_DU), du1 = rc(k, R_DU + 1);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { o.c1 += m_abs(d[j]); o.mag += m_abs(x0d[j]) + m_abs(x1d[j]); }
+      o.mag += dt * (T(2) * m_abs(v) + m_abs(u0) + m_abs(u1)) + m_abs(rc(k, R_CP)) + m_abs(rc(k, R_CP + 1));
+      o.dphi += T(2) * P.R[0] * u0 * du0 + T(2) * P.R[1] * u1 * du1;
+      if (k + 1 <= N - 1) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) o.dphi += T(2) * P.Q[j] * x1d[j] * nx[j];
+      }
+      row_limits(m_slack(u0 - P.dd_min), rc(k, R_V + V_DD_LO), du0, mu, tau, o);
+      row_limits(m_slack(P.dd_max - u0), rc(k, R_V + V_DD_HI), -du0, mu, tau, o);
+      const T ahi = (k == 0) ? st.a0_hi : P.a_max;
+      row_limits(m_slack(ahi - u1), rc(k, R_V + V_A_HI), -du1, mu, tau, o);
+      if (k == 0) row_limits(m_slack(u1 - st.a0_lo), rc(k, R_V + V_A_LO), du1, mu, tau, o);
+      row_limits(m_slack(x1a[2] - P.de_min), rc(k, R_V + V_DE_LO), nx[2], mu, tau, o);
+      row_limits(m_slack(P.de_max - x1a[2]), rc(k, R_V + V_DE_HI), -nx[2], mu, tau, o);
+      row_limits(m_slack(x1a[3] - P.v_min), rc(k, R_V + V_V_LO), nx[3], mu, tau, o);
+      row_limits(m_slack(P.v_max - x1a[3]), rc(k, R_V + V_V_HI), -nx[3], mu, tau, o);
+      const T sn1 = sx(k + 1, S_TR), cs1 = sx(k + 1, S_TR + 1);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, x1a[0], x1a[1], sn1, cs1, h, gx, gy, gp);
+        const T s = rc(k, R_S + j);
+        const T r = (h - P.r_sum) - s;
+        const T ds = gx * nx[0] + gy * nx[1] + gp * nx[4] + r;
+        o.c1 += m_resid(r, h);
+        row_limits(s, rc(k, R_V + V_OB0 + j), ds, mu, tau, o);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) o.step_inf = m_max(o.step_inf, m_abs(nx[j]));
+      o.step_inf = m_max(o.step_inf, m_max(m_abs(du0), m_abs(du1)));
+    }
+    const bool fin = m_finite(o.step_inf) && m_finite(o.dphi) && m_finite(o.a_p) && m_finite(o.a_d);
+    const bool allfin = w.all(fin);
+    o.a_p = w.min_nonneg(m_max(o.a_p, T(0))); o.a_d = w.min_nonneg(m_max(o.a_d, T(0)));
+    o.step_inf = w.max_nonneg(fin ? o.step_inf : T(0));
+    o.dphi = w.sum(o.dphi); o.c1 = w.sum(o.c1); o.mag = w.sum(o.mag);
+    if (!allfin) o.step_inf = T(NAN);     // the caller turns this into ST_NAN
+    return o;
+  }
+
+  // ---------------------------------------------------------------- phase F: merit difference phi(alpha) - phi(0) (lane = stage)
+  // trial_points: x^_{k+1} = x_{k+1} + al*dx_{k+1} and its trig (reused by the next linearisation when accepted).
+  MPC_HD void trial_points(T al) const {
+    const int N = P.N;
+    for (int k = lane; k < N; k += 32) {
+      T xb[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { xb[j] = sx(k + 1, S_XT + j) + al * rc(k, R_DX + j); sx(k + 1, S_XTT + j) = xb[j]; }
+      const Trig t = trig_of(xb[4] + sx(k + 1, S_XR + 4), xb[2] + sx(k + 1, S_XR + 2));
+      sx(k + 1, S_TRT) = t.sn; sx(k + 1, S_TRT + 1) = t.cs; sx(k + 1, S_TRT + 2) = t.tn;
+    }
+    w.sync();
+  }
+  // second-order correction: re-simulate the trial states from the trial controls,
+  //   x^_{k+1} = x^_k + dt f(x^_k, u_k + al*du_k) - (1 - al) d_k,
+  // so the dynamics defects shrink EXACTLY by (1 - al) (Maratos effect); the re-simulated step overwrites DX so that
+  // the multiplier / slack updates of commit() see it.  Serial in k, computed redundantly by every lane (rare path).
+  MPC_HD void trial_points_reshoot(T al) const {
+    const int N = P.N;
+    T xd[5], xaa[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { xd[j] = sx(0, S_XT + j); xaa[j] = xd[j] + sx(0, S_XR + j); }
+    Trig ta; ta.sn = sx(0, S_TR); ta.cs = sx(0, S_TR + 1); ta.tn = sx(0, S_TR + 2);
+    const T zero[5] = {T(0), T(0), T(0), T(0), T(0)};
+    for (int k = 0; k < N; ++k) {
+      const T nu0 = rc(k, R_U) + al * rc(k, R_DU), nu1 = rc(k, R_U + 1) + al * rc(k, R_DU + 1);
+      T roll[5];
+      defect(k, xd, zero, xaa[3], ta, nu0, nu1, roll);      // = xt^_k + dt f(x^_k, u^_k) + c_k
+      T xb[5], dxn[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        xb[j] = roll[j] - (T(1) - al) * rc(k, R_D + j);
+        dxn[j] = (xb[j] - sx(k + 1, S_XT + j)) / al;
+        xaa[j] = xb[j] + sx(k + 1, S_XR + j);
+        xd[j] = xb[j];
+      }
+      ta = trig_of(xaa[4], xaa[2]);
+      if (lane == (k & 31)) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { sx(k + 1, S_XTT + j) = xb[j]; rc(k, R_DX + j) = dxn[j]; }
+        sx(k + 1, S_TRT) = ta.sn; sx(k + 1, S_TRT + 1) = ta.cs; sx(k + 1, S_TRT + 2) = ta.tn;
+      }
+    }
+    w.sync();
+  }
+
+  // dphi: cost + barrier difference (term by term, no cancellation); c1: l1 infeasibility at the trial point;
+  // nz: magnitude sum of the terms (rounding-noise allowance); returns false if a slack would leave the interior.
+  MPC_HD bool trial_merit(const ProbState<T>& st, T al, bool reshoot, T& dphi, T& c1, T& nz) const {
+    const int N = P.N;
+    const T mu = st.mu;
+    dphi = T(0); c1 = T(0); nz = T(0);
+    bool ok = true;
+    T lg = T(0), lga = T(0);
+    auto lrow = [&](T num, T den) {
+      const T rt = num / den;
+      ok = ok && (rt > T(-1));
+      const T l = m_log1p(m_max(rt, T(-0.999999)));
+      lg += l; lga += m_abs(l);
+    };
+    for (int k = lane; k < N; k += 32) {
+      const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
+      const T du0 = al * rc(k, R_DU), du1 = al * rc(k, R_DU + 1);
+      const T nu0 = u0 + du0, nu1 = u1 + du1;
+      T xad[5], xbd[5], xba[5], dxb[5], x1d[5], x1a[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        xad[j] = sx(k, S_XTT + j);
+        xbd[j] = sx(k + 1, S_XTT + j);
+        xba[j] = xbd[j] + sx(k + 1, S_XR + j);
+        dxb[j] = al * rc(k, R_DX + j);
+        x1d[j] = sx(k + 1, S_XT + j);
+        x1a[j] = x1d[j] + sx(k + 1, S_XR + j);
+      }
+      Trig ta; ta.sn = sx(k, S_TRT); ta.cs = sx(k, S_TRT + 1); ta.tn = sx(k, S_TRT + 2);
+      T d[5];
+      if (reshoot) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) d[j] = (T(1) - al) * rc(k, R_D + j);
+      } else {
+        defect(k, xad, xbd, xad[3] + sx(k, S_XR + 3), ta, nu0, nu1, d);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) c1 += m_abs(d[j]);
+      {
+        const T t0 = P.R[0] * du0 * (T(2) * u0 + du0), t1 = P.R[1] * du1 * (T(2) * u1 + du1);
+        dphi += t0 + t1; nz += m_abs(t0) + m_abs(t1);
+      }
+      if (k + 1 <= N - 1) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const T t0 = P.Q[j] * dxb[j] * (T(2) * x1d[j] + dxb[j]);
+          dphi += t0; nz += m_abs(t0);
+        }
+      }
+      lrow(du0, m_slack(u0 - P.dd_min));
+      lrow(-du0, m_slack(P.dd_max - u0));
+      const T ahi = (k == 0) ? st.a0_hi : P.a_max;
+      lrow(-du1, m_slack(ahi - u1));
+      if (k == 0) lrow(du1, m_slack(u1 - st.a0_lo));
+      lrow(dxb[2], m_slack(x1a[2] - P.de_min));
+      lrow(-dxb[2], m_slack(P.de_max - x1a[2]));
+      lrow(dxb[3], m_slack(x1a[3] - P.v_min));
+      lrow(-dxb[3], m_slack(P.v_max - x1a[3]));
+      // obstacle rows: the slack moves with its own Newton step ds (from the OLD linearisation)
+      const T sn0 = sx(k + 1, S_TR), cs0 = sx(k + 1, S_TR + 1);
+      const T snb = sx(k + 1, S_TRT), csb = sx(k + 1, S_TRT + 1);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, x1a[0], x1a[1], sn0, cs0, h, gx, gy, gp);
+        const T s = rc(k, R_S + j);
+        const T r = (h - P.r_sum) - s;
+        const T ds = al * (gx * rc(k, R_DX) + gy * rc(k, R_DX + 1) + gp * rc(k, R_DX + 4) + r);
+        lrow(ds, s);
+        T hb, g1, g2, g3; obst(j, xba[0], xba[1], snb, csb, hb, g1, g2, g3);
+        c1 += m_resid((hb - P.r_sum) - (s + ds), hb);
+      }
+    }
+    dphi -= mu * lg;
+    nz += mu * lga;
+    ok = w.all(ok);
+    dphi = w.sum(dphi); c1 = w.sum(c1); nz = w.sum(nz);
+    return ok;
+  }
+
+  // ---------------------------------------------------------------- phase G: commit the step + complementarity statistics
+  MPC_HD void commit(ProbState<T>& st, T al, T ad, T& avg, T& cmax) const {
+    const int N = P.N;
+    const T mu = st.mu;
+    T sum = T(0); cmax = T(0);
+    for (int k = lane; k < N; k += 32) {
+      const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
+      const T du0 = rc(k, R_DU), du1 = rc(k, R_DU + 1);
+      T dx[5], x1a[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { dx[j] = rc(k, R_DX + j); x1a[j] = xa(k + 1, j); }
+      const T nu0 = u0 + al * du0, nu1 = u1 + al * du1;
+      T xn[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) xn[j] = sx(k + 1, S_XTT + j);
+      const T nde = xn[2] + sx(k + 1, S_XR + 2), nvv = xn[3] + sx(k + 1, S_XR + 3);
+      // multiplier update at the OLD point, complementarity product at the NEW point
+      auto upd = [&](int slot, T s, T ds, T snew) {
+        const T nu = rc(k, R_V + slot);
+        const T dnu = (mu - nu * s - nu * ds) / s;
+        const T nn = m_max(nu + ad * dnu, T(1e-30));
+        rc(k, R_V + slot) = nn;
+        const T c = snew * nn; sum += c; cmax = m_max(cmax, c);
+      };
+      upd(V_DD_LO, m_slack(u0 - P.dd_min), du0, m_slack(nu0 - P.dd_min));
+      upd(V_DD_HI, m_slack(P.dd_max - u0), -du0, m_slack(P.dd_max - nu0));
+      const T ahi = (k == 0) ? st.a0_hi : P.a_max;
+      upd(V_A_HI, m_slack(ahi - u1), -du1, m_slack(ahi - nu1));
+      if (k == 0) upd(V_A_LO, m_slack(u1 - st.a0_lo), du1, m_slack(nu1 - st.a0_lo));
+      upd(V_DE_LO, m_slack(x1a[2] - P.de_min), dx[2], m_slack(nde - P.de_min));
+      upd(V_DE_HI, m_slack(P.de_max - x1a[2]), -dx[2], m_slack(P.de_max - nde));
+      upd(V_V_LO, m_slack(x1a[3] - P.v_min), dx[3], m_slack(nvv - P.v_min));
+      upd(V_V_HI, m_slack(P.v_max - x1a[3]), -dx[3], m_slack(P.v_max - nvv));
+      const T sn1 = sx(k + 1, S_TR), cs1 = sx(k + 1, S_TR + 1);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, x1a[0], x1a[1], sn1, cs1, h, gx, gy, gp);
+        const T s = rc(k, R_S + j);
+        const T r = (h - P.r_sum) - s;
+        const T ds = gx * dx[0] + gy * dx[1] + gp * dx[4] + r;
+        const T snew = m_slack(s + al * ds);
+        upd(V_OB0 + j, s, ds, snew);
+        rc(k, R_S + j) = snew;
+      }
+      rc(k, R_U) = nu0; rc(k, R_U + 1) = nu1;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) sx(k + 1, S_XT + j) = xn[j];
+      sx(k + 1, S_TR) = sx(k + 1, S_TRT); sx(k + 1, S_TR + 1) = sx(k + 1, S_TRT + 1); sx(k + 1, S_TR + 2) = sx(k + 1, S_TRT + 2);
+    }
+    sum = w.sum(sum);
+    cmax = w.max_nonneg(m_max(cmax, T(0)));
+    avg = sum / T(10 * N + 1);
+    w.sync();
+  }
+
+  // ---------------------------------------------------------------- one SQP / interior-point iteration (uniform control flow)
+  MPC_HD void iterate(ProbState<T>& st) const {
+    if (st.done) return;
+    linearize(st);
+    if (!backward(P.hessian)) backward(HESS_GN);
+    forward_sweep();
+    FwdOut f = forward_stats(st);
+    if (!m_finite(f.step_inf) || !m_finite(f.dphi)) { st.status = ST_NAN; st.done = 1; return; }
+    // penalty parameter of the l1 merit
+    if (f.c1 > T(0)) {
+      const T need = f.dphi / (T(0.5) * f.c1);
+      if (need > st.rho) st.rho = need * T(1.5) + T(1);
+    }
+    const T slope = f.dphi - st.rho * f.c1;
+    const T epsm = m_eps(T(0));
+    T al = f.a_p;
+    bool accepted = false;
+    for (int t = 0; t < P.ls_max; ++t) {
+      T dphi, c1, nz;
+      trial_points(al);
+      bool ok = trial_merit(st, al, false, dphi, c1, nz);
+      T dm = dphi + st.rho * (c1 - f.c1);
+      T noise = T(8) * epsm * (nz + st.rho * f.mag);
+      if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; break; }
+      if (t == 0 && ok && m_finite(dm)) {
+        trial_points_reshoot(al);
+        ok = trial_merit(st, al, true, dphi, c1, nz);
+        dm = dphi + st.rho * (c1 - f.c1);
+        noise = T(8) * epsm * (nz + st.rho * f.mag);
+        if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; st.nsoc++; break; }
+        // the re-simulated step replaced DX: restore the Newton step for the shorter trials
+        forward_sweep();
+      }
+      al *= T(0.5);
+    }
+    if (!accepted) {
+      st.nfail++;
+      if (st.nfail >= 3) { st.status = ST_NOPROGRESS; st.done = 1; return; }
+      trial_points(al);        // the step is taken anyway (as in sqp_core.cuh): trial point for commit
+    } else {
+      st.nfail = 0;
+    }
+    T avg, cmax;
+    commit(st, al, f.a_d, avg, cmax);
+    st.d_al = al; st.d_ap = f.a_p; st.d_ad = f.a_d; st.d_c1 = f.c1; st.d_dphi = f.dphi;
+    st.iters++;
+    st.kkt = f.step_inf;
+    if (st.mu <= P.mu_min * T(1.0001) && al >= T(0.5) && al * f.step_inf <= P.tol_step && f.c1 <= P.tol_feas) {
+      st.status = ST_OPTIMAL; st.done = 1; return;
+    }
+    if (al >= T(0.5)) {
+      const T mu_new = m_max(P.mu_min, m_min(st.mu, P.mu_factor * avg));
+      if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
+      st.mu = mu_new;
+    }
+  }
+};
+
+}  // namespace mpcb200
