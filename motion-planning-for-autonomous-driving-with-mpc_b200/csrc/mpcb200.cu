@@ -104,8 +104,8 @@ __device__ __forceinline__ bool tile_is_bulk(int nvalid, int per_problem) {
 // One warp per ego instance; WPC warps (problems) per CTA.  All SQP iterations of a problem run inside the launch
 // (MODE_ONESHOT), or `n_iter` of them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
 template <typename T, int WPC>
-__global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const SolveArgs<T> a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
+  unsigned char* const smem_raw = mpc_dyn_smem;
   __shared__ __align__(8) uint64_t bar_io;
   __shared__ __align__(8) uint64_t bar_w[WPC];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const SolveArg
 
   const WarpCtx w;
   T obs[6];
-  WarpSolver<T> S(a.P, sm.slab(wid), obs, w);
+  WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   const bool need_xref = (a.mode != MODE_ITER);
   const bool need_warm = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
@@ -254,8 +254,8 @@ __device__ __forceinline__ void ref_window_rows(int i, int N, int Tlen, const do
 // The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631) for one ego per warp, no host
 // round trip between MPC steps: solve, record u_0, plant step + warm-start shift, next reference window.
 template <typename T, int WPC>
-__global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const LoopArgs<T> a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __grid_constant__ LoopArgs<T> a) {
+  unsigned char* const smem_raw = mpc_dyn_smem;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
   const WLayout L(N);
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const Lo
   double* my_U = sm.U(wid);
   const WarpCtx w;
   T obs[6];
-  WarpSolver<T> S(a.P, sm.slab(wid), obs, w);
+  WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   double x[5];
   for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];

@@ -111,40 +111,64 @@ struct LaneTab {
       if (i == 3 && j == 4) exw = 2;
       if (i == 2 && j == 3) exw = 4;
     }
+#pragma unroll
     for (int t = 0; t < 5; ++t) {
       c[t] = (j == 5) ? (R_D + t) : ((t == j) ? R_ONE : e_off(t, j));
       s1[t] = (i <= t) ? (6 * i + t) : (6 * t + i);
     }
-    int src[3] = {0, 0, 0}, n = 0;
-    for (int t = 0; t < 3; ++t) e[t] = R_ZERO;
-    for (int ll = 0; ll < 5; ++ll) {
-      if (e_off(ll, i) != R_ZERO && n < 3) { e[n] = e_off(ll, i); src[n] = ll; ++n; }
-    }
-    for (int t = 0; t < 3; ++t) s2[t] = 6 * src[t] + j;
+    // rows l with E[l][i] != 0:  i = 2: {4},  i = 3: {0, 1, 4},  i = 4: {0, 1}   (static indexing only: registers)
+    const int l0 = (i == 2) ? 4 : 0, l1 = 1, l2 = 4;
+    e[0] = (i >= 2) ? e_off(l0, i) : R_ZERO;
+    e[1] = (i >= 3) ? e_off(l1, i) : R_ZERO;
+    e[2] = (i == 3) ? e_off(l2, i) : R_ZERO;
+    s2[0] = 6 * l0 + j; s2[1] = 6 * l1 + j; s2[2] = 6 * l2 + j;
     s_m2j = 12 + j; s_m3j = 18 + j; s_m2i = 12 + i; s_m3i = 18 + i;
     const int r = lane < 5 ? lane : 0;
     fscale = (r == 2 || r == 3) ? 1 : 0;
+#pragma unroll
     for (int t = 0; t < 5; ++t) fc[t] = (r == 2) ? (R_KK + t) : (r == 3) ? (R_KK + 6 + t) : e_off(r, t);
     fc0 = (r == 2) ? (R_KK + 5) : (r == 3) ? (R_KK + 11) : R_ZERO;
   }
 };
 
+// The slab accessor.  On the device it indexes the CTA's dynamic shared memory by a 32-bit word offset, so every access
+// is an LDS/STS with immediate field offsets (a generic `T*` member made nvcc fall back to 64-bit generic LD/ST).
+#if defined(__CUDACC__)
+extern __shared__ __align__(128) unsigned char mpc_dyn_smem[];
+template <typename T>
+struct SlabRef {
+  int base;          // word offset of this problem's slab inside the dynamic shared memory
+  MPC_HD T& operator[](int i) const { return reinterpret_cast<T*>(mpc_dyn_smem)[base + i]; }
+};
+#else
+template <typename T>
+struct SlabRef {
+  T* p;
+  int base;
+  MPC_HD T& operator[](int i) const { return p[base + i]; }
+};
+#endif
+
 template <typename T>
 struct WarpSolver {
   const ParamsT<T>& P;
   const WLayout L;
-  T* sl;             // this problem's slab
+  const SlabRef<T> sl;   // this problem's slab
   const T* obs;      // obstacle circle centres (centre, front, rear) in the problem's shifted frame
   const WarpCtx& w;
   const int lane;
   const LaneTab tb;
 
-  MPC_HD WarpSolver(const ParamsT<T>& P_, T* slab, const T* obs_, const WarpCtx& w_)
+  MPC_HD WarpSolver(const ParamsT<T>& P_, const SlabRef<T>& slab, const T* obs_, const WarpCtx& w_)
       : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()) {}
 
   MPC_HD T& sx(int k, int f) const { return sl[L.o_state + ST_STRIDE * k + f]; }
   MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + REC_STRIDE * k + f]; }
   MPC_HD T xa(int k, int j) const { return sx(k, S_XT + j) + sx(k, S_XR + j); }
+  struct RecRef {        // one stage record (serial sweeps: every lane reads the same record)
+    const SlabRef<T>& s; int o;
+    MPC_HD T operator[](int f) const { return s[o + f]; }
+  };
 
   struct Trig { T sn, cs, tn; };
   MPC_HD Trig trig_of(T psi, T delta) const { Trig t; m_sincos(psi, &t.sn, &t.cs); t.tn = m_tan(delta); return t; }
@@ -369,7 +393,7 @@ struct WarpSolver {
     const T isj5 = ownf;
     bool ok = true;
     for (int k = N - 1; k >= 0; --k) {
-      const T* r = &rc(k, 0);
+      const RecRef r{sl, L.o_rec + REC_STRIDE * k};
       const T hterm = r[tb.hidx];
       const T c0 = r[tb.c[0]], c1 = r[tb.c[1]], c2 = r[tb.c[2]], c3 = r[tb.c[3]], c4 = r[tb.c[4]];
       const T e0 = r[tb.e[0]], e1 = r[tb.e[1]], e2 = r[tb.e[2]];
@@ -431,7 +455,7 @@ struct WarpSolver {
     const int row = lane < 5 ? lane : 0;
     T dx0 = T(0), dx1 = T(0), dx2 = T(0), dx3 = T(0), dx4 = T(0), mine = T(0);
     for (int k = 0; k < N; ++k) {
-      const T* r = &rc(k, 0);
+      const RecRef r{sl, L.o_rec + REC_STRIDE * k};
       const T acc = r[tb.fc0] + ((r[tb.fc[0]] * dx0 + r[tb.fc[1]] * dx1) + (r[tb.fc[2]] * dx2 + r[tb.fc[3]] * dx3) + r[tb.fc[4]] * dx4);
       const T nx = mine + scale * acc + r[R_D + row];
       dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);

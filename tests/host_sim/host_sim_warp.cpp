@@ -27,7 +27,7 @@ static void lane_body(int lane, void* arg) {
   Job<T>& J = *(Job<T>*)arg;
   WarpCtx w(J.hw, lane);
   T obs[6];
-  WarpSolver<T> S(J.P, J.slab, obs, w);
+  WarpSolver<T> S(J.P, SlabRef<T>{J.slab, 0}, obs, w);
   S.load(J.xref, J.X, J.U, J.cfg->obstacle, obs);
   ProbState<T> st;
   S.init(st);
