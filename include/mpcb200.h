@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MPCB200_ABI_VERSION 1
+#define MPCB200_ABI_VERSION 2
 
 enum { MPCB200_F32 = 0, MPCB200_F64 = 1 };
 enum { MPCB200_HESS_GAUSS_NEWTON = 0, MPCB200_HESS_EXACT = 1 };
@@ -61,6 +61,9 @@ typedef struct mpcb200_config {
   double mu0, mu_min, mu_factor;   /* barrier schedule */
   double tol_step, tol_feas;       /* convergence: inf-norm of the Newton step, l1 norm of the defects */
   double tau_min, bound_push;      /* fraction-to-the-boundary, initial interior push */
+  double acc_factor;               /* acceptable exit: acc_iters consecutive steps <= acc_factor * tol_step at mu_min */
+  int32_t acc_iters;
+  int32_t init_rollout;            /* 1: initial states = Euler rollout of the initial controls from X_0 (X warm start ignored) */
 } mpcb200_config;
 
 typedef struct mpcb200_handle mpcb200_handle;

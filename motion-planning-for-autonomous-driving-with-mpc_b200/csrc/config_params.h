@@ -1,7 +1,7 @@
 // config_params.h -- mpcb200_config (C ABI) -> ParamsT<T> (kernel constants), plus the defaults.
 #pragma once
 #include "../../include/mpcb200.h"
-#include "sqp_core.cuh"
+#include "mpc_types.cuh"
 
 namespace mpcb200 {
 
@@ -17,12 +17,13 @@ inline ParamsT<T> params_from_config(const mpcb200_config& c) {
   p.r_sum = (T)c.r_sum; p.ego_off = (T)c.ego_offset;
   p.mu0 = (T)c.mu0; p.mu_min = (T)c.mu_min; p.mu_factor = (T)c.mu_factor;
   p.tol_step = (T)c.tol_step; p.tol_feas = (T)c.tol_feas; p.tau_min = (T)c.tau_min; p.bound_push = (T)c.bound_push;
+  p.acc_factor = (T)c.acc_factor; p.acc_iters = c.acc_iters; p.init_rollout = c.init_rollout;
   return p;
 }
 
 inline void default_config(mpcb200_config* c, int N, int precision) {
   c->abi_version = MPCB200_ABI_VERSION; c->device = 0; c->N = N; c->max_batch = 4096;
-  c->precision = precision; c->hessian = MPCB200_HESS_EXACT; c->max_iter = 100; c->ls_max = 8;
+  c->precision = precision; c->hessian = MPCB200_HESS_GAUSS_NEWTON; c->max_iter = 100; c->ls_max = 8;
   c->dt = 0.1; c->l_wb = 2.5789128; c->l_fric = 2.578;
   const double Q[5] = {2.3, 2.3, 500.0, 0.1, 10.0}, R[2] = {2.0, 0.2};   // config_LF_ZAM_Over-1_1.yaml:19-31
   for (int i = 0; i < 5; ++i) c->Q[i] = Q[i];
@@ -33,8 +34,9 @@ inline void default_config(mpcb200_config* c, int N, int precision) {
   const double ob[6] = {-100.0, 0.0, -100.0, 0.0, -100.0, 0.0};
   for (int i = 0; i < 6; ++i) c->obstacle[i] = ob[i];
   c->mu0 = 0.1; c->mu_factor = 0.2; c->tau_min = 0.99; c->bound_push = 1e-2;
-  if (precision == MPCB200_F64) { c->mu_min = 1e-9; c->tol_step = 1e-8; c->tol_feas = 1e-8; }
-  else                          { c->mu_min = 1e-6; c->tol_step = 2e-5; c->tol_feas = 1e-4; }
+  if (precision == MPCB200_F64) { c->mu_min = 1e-9; c->tol_step = 1e-8; c->tol_feas = 1e-8; c->acc_factor = 100.0; }
+  else                          { c->mu_min = 1e-6; c->tol_step = 2e-5; c->tol_feas = 1e-4; c->acc_factor = 5.0; }
+  c->acc_iters = 4; c->init_rollout = 0;
 }
 
 }  // namespace mpcb200

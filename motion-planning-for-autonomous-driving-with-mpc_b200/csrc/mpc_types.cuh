@@ -1,0 +1,113 @@
+// mpc_types.cuh -- problem constants, per-problem solver state, status codes and math wrappers shared by the solver
+// core (warp_core.cuh), the kernels (mpcb200.cu) and the host-side test build (tests/host_sim).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD inline
+#endif
+
+namespace mpcb200 {
+
+// ------------------------------------------------------------------ status codes (mirror FORCESNLPsolver.h:70-106)
+enum : int {
+  ST_OPTIMAL = 1,        // converged
+  ST_MAXIT = 0,          // iteration limit
+  ST_NAN = -6,           // NaN/Inf met
+  ST_NOPROGRESS = -7,    // line search failed repeatedly
+  ST_INFEASIBLE_X0 = -8, // pinned stage violates a constraint (friction row infeasible / nonconvex, x0 inside obstacle)
+};
+
+enum : int { HESS_GN = 0, HESS_EXACT = 1 };
+
+template <typename T>
+struct ParamsT {
+  int N;
+  int max_iter;
+  int hessian;       // HESS_GN | HESS_EXACT (exact Lagrangian Hessian with adjoint multipliers, GN fallback)
+  int ls_max;        // max backtracking trials
+  T dt, l_wb, l_fric;
+  T Q[5], R[2];
+  T dd_min, dd_max, a_max, de_min, de_max, v_min, v_max;
+  T r_sum, ego_off;
+  T mu0, mu_min, mu_factor, tol_step, tol_feas, tau_min, bound_push;
+  T acc_factor; int acc_iters;   // acceptable-level exit (warp core)
+  int init_rollout;              // 1: initial states = Euler rollout of the initial controls from the pinned state
+};
+
+// per-problem scalars that persist across launches (one launch per SQP iteration mode)
+template <typename T>
+struct ProbState {
+  T mu, rho;
+  T a0_lo, a0_hi;     // stage-0 friction box (constants of the pinned stage)
+  T kkt;              // last step inf-norm (diagnostic)
+  T d_al, d_ap, d_ad, d_c1, d_dphi; int d_blk;   // diagnostics of the last iteration
+  int status, iters, done, nfail, nsoc, nacc;
+};
+
+// ------------------------------------------------------------------ math wrappers
+MPC_HD float m_sqrt(float x) { return sqrtf(x); }
+MPC_HD double m_sqrt(double x) { return sqrt(x); }
+MPC_HD float m_abs(float x) { return fabsf(x); }
+MPC_HD double m_abs(double x) { return fabs(x); }
+MPC_HD float m_max(float a, float b) { return fmaxf(a, b); }
+MPC_HD double m_max(double a, double b) { return fmax(a, b); }
+MPC_HD float m_min(float a, float b) { return fminf(a, b); }
+MPC_HD double m_min(double a, double b) { return fmin(a, b); }
+MPC_HD float m_log1p(float x) { return log1pf(x); }
+MPC_HD double m_log1p(double x) { return log1p(x); }
+MPC_HD float m_tan(float x) { return tanf(x); }
+MPC_HD double m_tan(double x) { return tan(x); }
+MPC_HD void m_sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+MPC_HD void m_sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+template <typename T> MPC_HD bool m_finite(T x) { return (x - x) == T(0); }
+// reciprocal / reciprocal square root used where a few ulp do not matter (barrier weights, step-length limits, merit
+// ratios): on the device one MUFU op (+ one Newton step for rsqrt) instead of the IEEE division / sqrt sequences with
+// their slow-path calls; float64 and the host build use the exact operations.
+MPC_HD float m_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / x;
+#endif
+}
+MPC_HD double m_rcp(double x) { return 1.0 / x; }
+MPC_HD float m_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * (1.5f - 0.5f * x * r * r);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+MPC_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+MPC_HD float m_eps(float) { return 6e-8f; }
+MPC_HD double m_eps(double) { return 1.2e-16; }
+// |r| with a dead zone at the rounding level of the distance h it was computed from: the slack residual of a far,
+// inactive obstacle row (lane following: dummy obstacle ~130 m away, quirk Q11) is pure rounding noise of h.
+template <typename T> MPC_HD T m_resid(T r, T h) { return m_max(m_abs(r) - T(8) * m_eps(T(0)) * h, T(0)); }
+// slack of a bound row computed from the primal value; floored at a few ulps of the bound so that an iterate that
+// rounds onto its bound (fp32: mu/nu can be below one ulp of x) gives a stiff but finite barrier weight.
+MPC_HD float m_slack(float x) { return fmaxf(x, 2.5e-7f); }
+MPC_HD double m_slack(double x) { return fmax(x, 1e-15); }
+
+// dual slots per stage k (u_k rows then x_{k+1} rows)
+enum : int { V_DD_LO = 0, V_DD_HI, V_A_HI, V_A_LO, V_DE_LO, V_DE_HI, V_V_LO, V_V_HI, V_OB0, V_OB1, V_OB2, NV = 11 };
+
+
+}  // namespace mpcb200

@@ -1,8 +1,8 @@
 // warp_core.cuh -- warp-cooperative nonlinear-MPC solver core: ONE WARP PER EGO INSTANCE (one NLP).
 //
 // Solves the NLP the reference hands to IPOPT each MPC step (/root/reference/MPC_Planner/optimizer.py:513-560;
-// constraints :373-411, bounds :413-491, cost :493-511) with the same primal-dual interior-point / SQP-type iteration
-// as sqp_core.cuh (same formulas, same globalisation), re-mapped onto 32 lanes:
+// constraints :373-411, bounds :413-491, cost :493-511) with a Gauss-Newton / Newton SQP-type primal-dual interior-point
+// iteration (l1-merit line search with second-order correction, monotone barrier) mapped onto 32 lanes:
 //
 //   * phases that are independent per stage -- linearisation of the Euler multiple-shooting defects
 //     (optimizer.py:380-382) and the 10 inequality rows per stage into the stage KKT block, step-length limits,
@@ -23,7 +23,7 @@
 // New code: the reference contains no solver of its own (it calls casadi/IPOPT).  The same source compiles for the
 // device (nvcc) and, through the fiber emulator in warp_ctx.cuh, for the host-side algorithm tests (tests/host_sim).
 #pragma once
-#include "sqp_core.cuh"
+#include "mpc_types.cuh"
 #include "warp_ctx.cuh"
 
 namespace mpcb200 {
@@ -32,7 +32,7 @@ namespace mpcb200 {
 // stage record k = 0..N-1  (terms of u_k, of the dynamics x_k -> x_{k+1} and of x_{k+1})
 enum : int {
   R_U = 0,      // 2  controls u_k
-  R_V = 2,      // 11 multipliers of the inequality rows (slot order of sqp_core.cuh: V_DD_LO ...)
+  R_V = 2,      // 11 multipliers of the inequality rows (slot order: V_DD_LO ... V_OB2, mpc_types.cuh)
   R_S = 13,     // 3  obstacle slacks
   R_CP = 16,    // 2  reference position increment rho_k - rho_{k+1} (from float64)
   R_E = 18,     // 6  off-identity entries of A_k: e03 e04 e13 e14 e42 e43
@@ -158,9 +158,10 @@ struct WarpSolver {
   const WarpCtx& w;
   const int lane;
   const LaneTab tb;
+  const T il_wb;     // 1 / wheelbase
 
   MPC_HD WarpSolver(const ParamsT<T>& P_, const SlabRef<T>& slab, const T* obs_, const WarpCtx& w_)
-      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()) {}
+      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()), il_wb(T(1) / P_.l_wb) {}
 
   MPC_HD T& sx(int k, int f) const { return sl[L.o_state + ST_STRIDE * k + f]; }
   MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + REC_STRIDE * k + f]; }
@@ -178,8 +179,9 @@ struct WarpSolver {
     const T sg = (j == 0) ? T(0) : (j == 1 ? T(1) : T(-1));
     const T o = sg * P.ego_off;
     const T dx = px + o * cs - obs[2 * j], dy = py + o * sn - obs[2 * j + 1];
-    h = m_sqrt(dx * dx + dy * dy);
-    const T ih = T(1) / m_max(h, T(1e-12));
+    const T d2 = m_max(dx * dx + dy * dy, T(1e-24));
+    const T ih = m_rsqrt(d2);
+    h = d2 * ih;
     gx = dx * ih; gy = dy * ih;
     gp = o * (gy * cs - gx * sn);
   }
@@ -191,7 +193,7 @@ struct WarpSolver {
     d[1] = (x0d[1] - x1d[1]) + dt * v * t.sn + rc(k, R_CP + 1);
     d[2] = (x0d[2] - x1d[2]) + dt * u0 + (sx(k, S_XR + 2) - sx(k + 1, S_XR + 2));
     d[3] = (x0d[3] - x1d[3]) + dt * u1 + (sx(k, S_XR + 3) - sx(k + 1, S_XR + 3));
-    d[4] = (x0d[4] - x1d[4]) + dt * v * t.tn / P.l_wb + (sx(k, S_XR + 4) - sx(k + 1, S_XR + 4));
+    d[4] = (x0d[4] - x1d[4]) + dt * v * t.tn * il_wb + (sx(k, S_XR + 4) - sx(k + 1, S_XR + 4));
   }
 
   // ---------------------------------------------------------------- problem I/O (float64 row-major arrays of ONE problem)
@@ -214,6 +216,23 @@ struct WarpSolver {
       }
     }
     w.sync();
+    if (P.init_rollout) {
+      // single-shooting start: x_{k+1} = x_k + dt f(x_k, u_k) from the pinned state (float64, every lane redundantly;
+      // lane k % 32 keeps stage k+1).  The caller's X rows are ignored.
+      double x[5];
+      for (int j = 0; j < 5; ++j) x[j] = xref[j];
+      for (int k = 0; k < N; ++k) {
+        const double u0 = Uin[2 * k], u1 = Uin[2 * k + 1];
+        const double v = x[3], sn = sin(x[4]), cs = cos(x[4]), tn = tan(x[2]);
+        x[0] += (double)P.dt * v * cs; x[1] += (double)P.dt * v * sn; x[2] += (double)P.dt * u0; x[3] += (double)P.dt * u1;
+        x[4] += (double)P.dt * v * tn / (double)P.l_wb;
+        if (lane == (k & 31)) {
+          const double* rho = xref + 5 * ((k + 2 < N) ? (k + 2) : N);
+          for (int j = 0; j < 5; ++j) sx(k + 1, S_XT + j) = (T)(x[j] - rho[j]);
+        }
+      }
+      w.sync();
+    }
   }
   MPC_HD void store(const double* xref, double* Xout, double* Uout) const {
     const int N = P.N;
@@ -231,7 +250,7 @@ struct WarpSolver {
   // trig cache.  Every lane ends with the same (uniform) ProbState.
   MPC_HD void init(ProbState<T>& st) const {
     const int N = P.N;
-    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.kkt = T(0);
+    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.kkt = T(0);
     st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
     const T de0 = xa(0, 2), v0 = xa(0, 3);
     const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
@@ -316,7 +335,7 @@ struct WarpSolver {
       const T sec2 = T(1) + t0.tn * t0.tn;
       rc(k, R_E + E03) = dt * t0.cs; rc(k, R_E + E04) = -dt * v * t0.sn;
       rc(k, R_E + E13) = dt * t0.sn; rc(k, R_E + E14) = dt * v * t0.cs;
-      rc(k, R_E + E42) = dt * v * sec2 / P.l_wb; rc(k, R_E + E43) = dt * t0.tn / P.l_wb;
+      rc(k, R_E + E42) = dt * v * sec2 * il_wb; rc(k, R_E + E43) = dt * t0.tn * il_wb;
       T d[5];
       defect(k, x0d, x1d, v, t0, u0, u1, d);
 #pragma unroll
@@ -330,17 +349,17 @@ struct WarpSolver {
         for (int j = 0; j < 5; ++j) { const T gq = T(2) * P.Q[j] * x1d[j]; hd[j] = T(2) * P.Q[j]; g[j] = gq; lc[j] = gq; }
       }
       {
-        const T slo = m_slack(x1a[2] - P.de_min), shi = m_slack(P.de_max - x1a[2]);
+        const T ilo = m_rcp(m_slack(x1a[2] - P.de_min)), ihi = m_rcp(m_slack(P.de_max - x1a[2]));
         const T vlo = rc(k, R_V + V_DE_LO), vhi = rc(k, R_V + V_DE_HI);
-        hd[2] += vlo / slo + vhi / shi;
-        g[2] += -mu / slo + mu / shi;
+        hd[2] += vlo * ilo + vhi * ihi;
+        g[2] += mu * (ihi - ilo);
         lc[2] += -vlo + vhi;
       }
       {
-        const T slo = m_slack(x1a[3] - P.v_min), shi = m_slack(P.v_max - x1a[3]);
+        const T ilo = m_rcp(m_slack(x1a[3] - P.v_min)), ihi = m_rcp(m_slack(P.v_max - x1a[3]));
         const T vlo = rc(k, R_V + V_V_LO), vhi = rc(k, R_V + V_V_HI);
-        hd[3] += vlo / slo + vhi / shi;
-        g[3] += -mu / slo + mu / shi;
+        hd[3] += vlo * ilo + vhi * ihi;
+        g[3] += mu * (ihi - ilo);
         lc[3] += -vlo + vhi;
       }
       T h01 = T(0), h04 = T(0), h14 = T(0);
@@ -351,8 +370,9 @@ struct WarpSolver {
         T s = rc(k, R_S + j);
         if (h - P.r_sum > s) { s = h - P.r_sum; rc(k, R_S + j) = s; }
         const T nu = rc(k, R_V + V_OB0 + j);
-        const T wgt = nu / s, r = (h - P.r_sum) - s;
-        const T cg = -(mu / s - wgt * r);
+        const T is = m_rcp(s);
+        const T wgt = nu * is, r = (h - P.r_sum) - s;
+        const T cg = -(mu * is - wgt * r);
         hd[0] += wgt * gx * gx; h01 += wgt * gx * gy; h04 += wgt * gx * gp;
         hd[1] += wgt * gy * gy; h14 += wgt * gy * gp; hd[4] += wgt * gp * gp;
         g[0] += cg * gx; g[1] += cg * gy; g[4] += cg * gp;
@@ -364,17 +384,17 @@ struct WarpSolver {
       for (int j = 0; j < 5; ++j) { rc(k, R_GX + j) = g[j]; rc(k, R_LC + j) = lc[j]; }
       // control terms
       {
-        const T slo = m_slack(u0 - P.dd_min), shi = m_slack(P.dd_max - u0);
-        T Ru0 = T(2) * P.R[0] + rc(k, R_V + V_DD_LO) / slo + rc(k, R_V + V_DD_HI) / shi;
-        T ru0 = T(2) * P.R[0] * u0 - mu / slo + mu / shi;
+        const T ilo = m_rcp(m_slack(u0 - P.dd_min)), ihi = m_rcp(m_slack(P.dd_max - u0));
+        T Ru0 = T(2) * P.R[0] + rc(k, R_V + V_DD_LO) * ilo + rc(k, R_V + V_DD_HI) * ihi;
+        T ru0 = T(2) * P.R[0] * u0 + mu * (ihi - ilo);
         const T ahi = (k == 0) ? st.a0_hi : P.a_max;
-        const T sh = m_slack(ahi - u1);
-        T Ru1 = T(2) * P.R[1] + rc(k, R_V + V_A_HI) / sh;
-        T ru1 = T(2) * P.R[1] * u1 + mu / sh;
+        const T ish = m_rcp(m_slack(ahi - u1));
+        T Ru1 = T(2) * P.R[1] + rc(k, R_V + V_A_HI) * ish;
+        T ru1 = T(2) * P.R[1] * u1 + mu * ish;
         if (k == 0) {
-          const T sl_ = m_slack(u1 - st.a0_lo);
-          Ru1 += rc(k, R_V + V_A_LO) / sl_;
-          ru1 -= mu / sl_;
+          const T isl = m_rcp(m_slack(u1 - st.a0_lo));
+          Ru1 += rc(k, R_V + V_A_LO) * isl;
+          ru1 -= mu * isl;
         }
         rc(k, R_RU) = Ru0; rc(k, R_RU + 1) = Ru1; rc(k, R_RU + 2) = ru0; rc(k, R_RU + 3) = ru1;
       }
@@ -392,12 +412,23 @@ struct WarpSolver {
     const T ownf = (T)tb.own;
     const T isj5 = ownf;
     bool ok = true;
+    // per-lane record pointers, bumped one record per stage (one IADD each instead of index arithmetic per load)
+    const int last = L.o_rec + REC_STRIDE * (N - 1);
+    const T* ph = &sl[last + tb.hidx];
+    const T* pc0 = &sl[last + tb.c[0]]; const T* pc1 = &sl[last + tb.c[1]]; const T* pc2 = &sl[last + tb.c[2]];
+    const T* pc3 = &sl[last + tb.c[3]]; const T* pc4 = &sl[last + tb.c[4]];
+    const T* pe0 = &sl[last + tb.e[0]]; const T* pe1 = &sl[last + tb.e[1]]; const T* pe2 = &sl[last + tb.e[2]];
+    const T* pr = &sl[last];
+    T* pk = &sl[last + R_KK + tb.j];
     for (int k = N - 1; k >= 0; --k) {
       const RecRef r{sl, L.o_rec + REC_STRIDE * k};
-      const T hterm = r[tb.hidx];
-      const T c0 = r[tb.c[0]], c1 = r[tb.c[1]], c2 = r[tb.c[2]], c3 = r[tb.c[3]], c4 = r[tb.c[4]];
-      const T e0 = r[tb.e[0]], e1 = r[tb.e[1]], e2 = r[tb.e[2]];
-      const T Ru0 = r[R_RU], Ru1 = r[R_RU + 1], ru0 = r[R_RU + 2], ru1 = r[R_RU + 3];
+      const T hterm = *ph;
+      const T c0 = *pc0, c1 = *pc1, c2 = *pc2, c3 = *pc3, c4 = *pc4;
+      const T e0 = *pe0, e1 = *pe1, e2 = *pe2;
+      const T Ru0 = pr[R_RU], Ru1 = pr[R_RU + 1], ru0 = pr[R_RU + 2], ru1 = pr[R_RU + 3];
+      T* const pkk = pk;
+      ph -= REC_STRIDE; pc0 -= REC_STRIDE; pc1 -= REC_STRIDE; pc2 -= REC_STRIDE; pc3 -= REC_STRIDE; pc4 -= REC_STRIDE;
+      pe0 -= REC_STRIDE; pe1 -= REC_STRIDE; pe2 -= REC_STRIDE; pr -= REC_STRIDE; pk -= REC_STRIDE;
       Pij += hterm;                                   // x_{k+1} terms
       // round 1: control block + M = [P|p] * Atilde
       const T p22 = w.shfl(Pij, 14), p23 = w.shfl(Pij, 15), p33 = w.shfl(Pij, 21);
@@ -409,7 +440,8 @@ struct WarpSolver {
       if (hess == HESS_EXACT) {
         if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) { ok = false; break; }      // uniform across lanes
       }
-      const T idet = T(1) / det;
+      T idet = m_rcp(det);
+      idet = idet * (T(2) - det * idet);              // one Newton step: the gains need the full precision
       const T I00 = G11 * idet, I01 = -G01 * idet, I11 = G00 * idet;
       // round 2: H = B^T M (+ ru on the affine column), Pn = A^T M - H^T G^-1 H
       const T m2j = w.shfl(M, tb.s_m2j), m3j = w.shfl(M, tb.s_m3j);
@@ -419,7 +451,7 @@ struct WarpSolver {
       const T K0j = -(I00 * H0j + I01 * H1j), K1j = -(I01 * H0j + I11 * H1j);
       const T H0i = dt * m2i, H1i = dt * m3i;
       T Pn = (M + e0 * r0) + (e1 * r1 + e2 * r2) + (H0i * K0j + H1i * K1j);
-      if (lane < 6) { rc(k, R_KK + tb.j) = K0j; rc(k, R_KK + 6 + tb.j) = K1j; }
+      if (lane < 6) { pkk[0] = K0j; pkk[6] = K1j; }
       if (hess == HESS_EXACT) {
         // adjoint multipliers lam_{k+1} (every lane keeps the 5-vector), then
         // + dt * sum_i lam_{k+1,i} * hess f_i(x_k) on the (delta, v, psi) block of P_k
@@ -431,8 +463,8 @@ struct WarpSolver {
         T ex = T(0);
         if (tb.exw == 1) ex = dt * (-lam[0] * v * cs - lam[1] * v * sn);
         if (tb.exw == 2) ex = dt * (-lam[0] * sn + lam[1] * cs);
-        if (tb.exw == 3) ex = dt * lam[4] * T(2) * v / P.l_wb * sec2 * tn;
-        if (tb.exw == 4) ex = dt * lam[4] * sec2 / P.l_wb;
+        if (tb.exw == 3) ex = dt * lam[4] * T(2) * v * il_wb * sec2 * tn;
+        if (tb.exw == 4) ex = dt * lam[4] * sec2 * il_wb;
         Pn += ex;
         const T f03 = r[R_E + E03], f04 = r[R_E + E04], f13 = r[R_E + E13], f14 = r[R_E + E14];
         const T f42 = r[R_E + E42], f43 = r[R_E + E43];
@@ -454,35 +486,47 @@ struct WarpSolver {
     const T scale = tb.fscale ? dt : T(1);
     const int row = lane < 5 ? lane : 0;
     T dx0 = T(0), dx1 = T(0), dx2 = T(0), dx3 = T(0), dx4 = T(0), mine = T(0);
+    const T* pf0 = &sl[L.o_rec + tb.fc[0]]; const T* pf1 = &sl[L.o_rec + tb.fc[1]]; const T* pf2 = &sl[L.o_rec + tb.fc[2]];
+    const T* pf3 = &sl[L.o_rec + tb.fc[3]]; const T* pf4 = &sl[L.o_rec + tb.fc[4]]; const T* pfc = &sl[L.o_rec + tb.fc0];
+    T* pd = &sl[L.o_rec + row];
     for (int k = 0; k < N; ++k) {
-      const RecRef r{sl, L.o_rec + REC_STRIDE * k};
-      const T acc = r[tb.fc0] + ((r[tb.fc[0]] * dx0 + r[tb.fc[1]] * dx1) + (r[tb.fc[2]] * dx2 + r[tb.fc[3]] * dx3) + r[tb.fc[4]] * dx4);
-      const T nx = mine + scale * acc + r[R_D + row];
+      const T acc = *pfc + ((*pf0 * dx0 + *pf1 * dx1) + (*pf2 * dx2 + *pf3 * dx3) + *pf4 * dx4);
+      const T nx = mine + scale * acc + pd[R_D];
+      T* const pdd = pd;
+      pf0 += REC_STRIDE; pf1 += REC_STRIDE; pf2 += REC_STRIDE; pf3 += REC_STRIDE; pf4 += REC_STRIDE; pfc += REC_STRIDE; pd += REC_STRIDE;
       dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);
       mine = nx;
-      if (lane < 5) rc(k, R_DX + lane) = nx;
-      if (lane == 2) rc(k, R_DU) = acc;
-      if (lane == 3) rc(k, R_DU + 1) = acc;
+      if (lane < 5) pdd[R_DX] = nx;
+      if (lane == 2 || lane == 3) pdd[R_DU - 2] = acc;
     }
     w.sync();
   }
 
   // ---------------------------------------------------------------- phase E: step-length limits, merit slope (lane = stage)
-  struct FwdOut { T a_p, a_d, dphi, c1, step_inf, mag; };
+  // a_p / a_d hold, until the final reduction, the LARGEST relative decrease -ds/s and -dnu/nu over the rows; the
+  // fraction-to-the-boundary step lengths are then min(1, tau / that) -- one division per iteration instead of per row.
+  struct FwdOut { T a_p, a_d, dphi, c1, step_inf, mag; int blk, cur; };
 
   MPC_HD void row_limits(T s, T nu, T ds, T mu, T tau, FwdOut& o) const {
-    const T dnu = (mu - nu * s - nu * ds) / s;
-    if (ds < T(0)) o.a_p = m_min(o.a_p, -tau * s / ds);
-    if (dnu < T(0)) o.a_d = m_min(o.a_d, -tau * nu / dnu);
-    o.dphi += -mu * ds / s;
+    const T is = m_rcp(s), inu = m_rcp(nu);
+    const T t = ds * is;                                  // ds / s
+    const T q = (mu * is) * inu - T(1) - t;               // dnu / nu  with dnu = (mu - nu*s - nu*ds) / s
+#ifdef MPC_DIAG
+    if (-t > o.a_p) o.blk = o.cur;
+    o.cur++;
+#endif
+    o.a_p = m_max(o.a_p, -t);
+    o.a_d = m_max(o.a_d, -q);
+    o.dphi -= mu * t;
   }
 
   MPC_HD FwdOut forward_stats(const ProbState<T>& st) const {
     const int N = P.N;
     const T dt = P.dt, mu = st.mu;
     const T tau = m_max(P.tau_min, T(1) - mu);
-    FwdOut o; o.a_p = T(1); o.a_d = T(1); o.dphi = T(0); o.c1 = T(0); o.step_inf = T(0); o.mag = T(0);
+    FwdOut o; o.a_p = T(0); o.a_d = T(0); o.dphi = T(0); o.c1 = T(0); o.step_inf = T(0); o.mag = T(0); o.blk = -1; o.cur = 0;
     for (int k = lane; k < N; k += 32) {
+      o.cur = 16 * k;
       T x0d[5], x1d[5], x1a[5], nx[5], d[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
@@ -525,7 +569,14 @@ struct WarpSolver {
     }
     const bool fin = m_finite(o.step_inf) && m_finite(o.dphi) && m_finite(o.a_p) && m_finite(o.a_d);
     const bool allfin = w.all(fin);
-    o.a_p = w.min_nonneg(m_max(o.a_p, T(0))); o.a_d = w.min_nonneg(m_max(o.a_d, T(0)));
+#ifdef MPC_DIAG
+    { const T mine = o.a_p; const T mx = w.max_nonneg(m_max(o.a_p, T(0))); int code = (mine == mx) ? o.blk : -1;
+      for (int m = 16; m; m >>= 1) { const int other = w.shfl_xor(code, m); code = code > other ? code : other; }
+      o.blk = code; }
+#endif
+    o.a_p = w.max_nonneg(m_max(o.a_p, T(0))); o.a_d = w.max_nonneg(m_max(o.a_d, T(0)));
+    o.a_p = (o.a_p > tau) ? tau / o.a_p : T(1);
+    o.a_d = (o.a_d > tau) ? tau / o.a_d : T(1);
     o.step_inf = w.max_nonneg(fin ? o.step_inf : T(0));
     o.dphi = w.sum(o.dphi); o.c1 = w.sum(o.c1); o.mag = w.sum(o.mag);
     if (!allfin) o.step_inf = T(NAN);     // the caller turns this into ST_NAN
@@ -587,7 +638,7 @@ struct WarpSolver {
     bool ok = true;
     T lg = T(0), lga = T(0);
     auto lrow = [&](T num, T den) {
-      const T rt = num / den;
+      const T rt = num * m_rcp(den);
       ok = ok && (rt > T(-1));
       const T l = m_log1p(m_max(rt, T(-0.999999)));
       lg += l; lga += m_abs(l);
@@ -676,7 +727,7 @@ struct WarpSolver {
       // multiplier update at the OLD point, complementarity product at the NEW point
       auto upd = [&](int slot, T s, T ds, T snew) {
         const T nu = rc(k, R_V + slot);
-        const T dnu = (mu - nu * s - nu * ds) / s;
+        const T dnu = (mu - nu * s - nu * ds) * m_rcp(s);
         const T nn = m_max(nu + ad * dnu, T(1e-30));
         rc(k, R_V + slot) = nn;
         const T c = snew * nn; sum += c; cmax = m_max(cmax, c);
@@ -720,13 +771,14 @@ struct WarpSolver {
     forward_sweep();
     FwdOut f = forward_stats(st);
     if (!m_finite(f.step_inf) || !m_finite(f.dphi)) { st.status = ST_NAN; st.done = 1; return; }
-    // penalty parameter of the l1 merit
-    if (f.c1 > T(0)) {
+    // penalty parameter of the l1 merit (left alone once the infeasibility is at its rounding-noise floor: dividing by
+    // a noise-level c1 would blow rho up and hand the line search to the noise)
+    const T epsm = m_eps(T(0));
+    if (f.c1 > T(8) * epsm * f.mag) {
       const T need = f.dphi / (T(0.5) * f.c1);
       if (need > st.rho) st.rho = need * T(1.5) + T(1);
     }
     const T slope = f.dphi - st.rho * f.c1;
-    const T epsm = m_eps(T(0));
     T al = f.a_p;
     bool accepted = false;
     for (int t = 0; t < P.ls_max; ++t) {
@@ -750,20 +802,26 @@ struct WarpSolver {
     if (!accepted) {
       st.nfail++;
       if (st.nfail >= 3) { st.status = ST_NOPROGRESS; st.done = 1; return; }
-      trial_points(al);        // the step is taken anyway (as in sqp_core.cuh): trial point for commit
+      trial_points(al);        // the (short) step is taken anyway: trial point for commit
     } else {
       st.nfail = 0;
     }
     T avg, cmax;
     commit(st, al, f.a_d, avg, cmax);
-    st.d_al = al; st.d_ap = f.a_p; st.d_ad = f.a_d; st.d_c1 = f.c1; st.d_dphi = f.dphi;
+    st.d_al = al; st.d_ap = f.a_p; st.d_ad = f.a_d; st.d_c1 = f.c1; st.d_dphi = f.dphi; st.d_blk = f.blk;
     st.iters++;
     st.kkt = f.step_inf;
-    if (st.mu <= P.mu_min * T(1.0001) && al >= T(0.5) && al * f.step_inf <= P.tol_step && f.c1 <= P.tol_feas) {
-      st.status = ST_OPTIMAL; st.done = 1; return;
+    if (st.mu <= P.mu_min * T(1.0001) && f.c1 <= P.tol_feas) {
+      if (al >= T(0.5) && al * f.step_inf <= P.tol_step) { st.status = ST_OPTIMAL; st.done = 1; return; }
+      // "acceptable" exit (IPOPT's acceptable_tol / acceptable_iter idea): with strongly active rows the barrier
+      // weights reach 1/mu_min and the Newton step has a rounding-noise floor above tol_step; a run of steps at that
+      // floor is convergence, not progress
+      if (al * f.step_inf <= P.acc_factor * P.tol_step) { if (++st.nacc >= P.acc_iters) { st.status = ST_OPTIMAL; st.done = 1; return; } }
+      else st.nacc = 0;
     }
     if (al >= T(0.5)) {
-      const T mu_new = m_max(P.mu_min, m_min(st.mu, P.mu_factor * avg));
+      // monotone barrier update, linear (mu_factor) far out and superlinear (avg^1.5, as IPOPT's theta_mu) close in
+      const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(P.mu_factor * avg, avg * m_sqrt(avg))));
       if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
       st.mu = mu_new;
     }

@@ -136,7 +136,7 @@ def _require_cuda():
 class B200Optimizer(_Base):
     """Batched nonlinear-MPC optimizer on one B200.  `optimize()` keeps the reference's contract (B = 1)."""
 
-    def __init__(self, configuration, init_values, predict_horizon, precision="f32", hessian="exact",
+    def __init__(self, configuration, init_values, predict_horizon, precision="f32", hessian="gn",
                  max_batch=4096, device=None, max_iter=100, **solver_opts):
         super(B200Optimizer, self).__init__(configuration, init_values, predict_horizon)
         torch = _require_cuda()

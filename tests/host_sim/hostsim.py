@@ -17,7 +17,8 @@ class Config(C.Structure):
                  ("delta_min", C.c_double), ("delta_max", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double),
                  ("r_sum", C.c_double), ("ego_offset", C.c_double), ("obstacle", C.c_double * 6),
                  ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_factor", C.c_double), ("tol_step", C.c_double),
-                 ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double)])
+                 ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double), ("acc_factor", C.c_double),
+                 ("acc_iters", C.c_int32), ("init_rollout", C.c_int32)])
 
 
 _lib = None
@@ -28,9 +29,10 @@ def lib():
     if _lib is None:
         so = os.path.join(HERE, "libhostsim.so")
         src = os.path.join(HERE, "host_sim.cpp")
-        core = os.path.join(HERE, "..", "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc", "sqp_core.cuh")
-        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], cwd=HERE)
+        csrc = os.path.join(HERE, "..", "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
+        if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMPC_DIAG", "-shared", "-fPIC", "-o", so, src], cwd=HERE)
         _lib = C.CDLL(so)
     return _lib
 

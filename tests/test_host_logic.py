@@ -1,5 +1,6 @@
-"""CPU tests of the host side and of the solver core's ALGORITHM (tests/host_sim = the device code of the CUDA kernels
-compiled with g++; test tooling only -- the product has no CPU path)."""
+"""CPU tests of the host side and of the solver core's ALGORITHM and LANE MAPPINGS (tests/host_sim = csrc/warp_core.cuh,
+the device code of the warp-per-problem CUDA kernels, compiled with g++ on a 32-fiber lock-step warp emulator; test
+tooling only -- the product has no CPU path)."""
 import os
 
 import numpy as np
@@ -12,7 +13,7 @@ from mpc_b200 import optimizer as O
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _cfg(sc, N, prec, hess=1):
+def _cfg(sc, N, prec, hess=0, **opts):
     circles, r_sum, off = O.obstacle_circles_and_radius(sc.static_obstacle)
     cfg = hostsim.default_config(N, prec)
     cfg.hessian = hess
@@ -24,6 +25,8 @@ def _cfg(sc, N, prec, hess=1):
     cfg.r_sum, cfg.ego_offset = r_sum, off
     for j in range(3):
         cfg.obstacle[2 * j], cfg.obstacle[2 * j + 1] = circles[j]
+    for k, v in opts.items():
+        setattr(cfg, k, v)
     return cfg
 
 
@@ -67,7 +70,7 @@ def test_collision_avoidance_solution_is_a_kkt_point_of_the_reference_nlp():
     from oracle import nlp, ipm
     N, B = 30, 3
     sc, x0, xref, X, U = mpc_b200.make_batch("ZAM_Over-1_1_CA", B, N, 20261018)
-    Xs, Us, st, it, _ = hostsim.solve(_cfg(sc, N, 1), xref, X, U)
+    Xs, Us, st, it, _ = hostsim.solve(_cfg(sc, N, 1, max_iter=200), xref, X, U)
     assert (st == 1).all()
     for b in range(B):
         d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
@@ -76,6 +79,25 @@ def test_collision_avoidance_solution_is_a_kkt_point_of_the_reference_nlp():
         assert (nlp.g_fun(d, w)[1 + 5 * (N + 1):] >= d.r_sum - 1e-7).all()      # keeps >= 3.3 m from the obstacle
         r = ipm.solve(d, w)                                                      # oracle warm-started at that point
         assert r["status"] == 1 and np.abs(r["w"] - w).max() < 1e-5
+
+
+def test_rollout_start_reaches_the_same_lane_following_optimum():
+    """init_rollout = 1 replaces the caller's X warm start by the Euler rollout of U from the pinned state."""
+    N, B = 30, 4
+    sc, x0, xref, X, U = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 20261017)
+    Xa, Ua, sta, _, _ = hostsim.solve(_cfg(sc, N, 1), xref, X, U)
+    Xb, Ub, stb, _, _ = hostsim.solve(_cfg(sc, N, 1, init_rollout=1), xref, np.full_like(X, 1e3), U)     # X is ignored
+    assert (sta == 1).all() and (stb == 1).all()
+    assert np.abs(Ua - Ub).max() < 1e-6 and np.abs(Xa - Xb).max() < 1e-6
+
+
+def test_exact_hessian_falls_back_and_agrees_with_gauss_newton():
+    N, B = 30, 4
+    sc, x0, xref, X, U = mpc_b200.make_batch("USA_Lanker-2_18_T-1_LF", B, 50, 20261019)
+    Xa, Ua, sta, _, _ = hostsim.solve(_cfg(sc, 50, 1, hess=0), xref, X, U)
+    Xb, Ub, stb, _, _ = hostsim.solve(_cfg(sc, 50, 1, hess=1), xref, X, U)
+    assert (sta == 1).all() and (stb == 1).all()
+    assert np.abs(Ua - Ub).max() < 1e-6 and np.abs(Xa - Xb).max() < 1e-6
 
 
 def test_scenarios_and_batch_generator():
