@@ -41,9 +41,9 @@ enum : int {
   R_ONE = 30,   // 1  constant 1
   R_H = 31,     // 8  Hessian of the x_{k+1} terms: h00 h01 h04 h11 h14 h44 h22 h33
   R_GX = 39,    // 5  gradient of the x_{k+1} terms (barrier gradient at the current mu)
-  R_RU = 44,    // 4  Ru0 Ru1 ru0 ru1 (control Hessian diagonal / gradient incl. barrier terms)
+  R_RU = 44,    // 4  Ru0 Ru1 ru0/dt ru1/dt (control Hessian diagonal / gradient incl. barrier terms)
   R_LC = 48,    // 5  multiplier-weighted gradient of the x_{k+1} terms (adjoint recursion, exact Hessian)
-  R_KK = 53,    // 12 gains: K0[0..4] k0 K1[0..4] k1
+  R_KK = 53,    // 12 gains times dt: dt*(K0[0..4] k0 K1[0..4] k1)
   R_DX = 65,    // 5  step dx_{k+1}
   R_DU = 70,    // 2  step du_k
   REC_STRIDE = 73
@@ -92,7 +92,6 @@ struct LaneTab {
   int s2[3];       // source lanes of M[l_t][j]
   int s_m2j, s_m3j, s_m2i, s_m3i;
   int fc[5], fc0;  // forward sweep, lanes 0..4: coefficients of row `lane` and of the constant term
-  int fscale;      // 1: rows 2,3 (acc is du, scaled by dt), 0: rows 0,1,4
   MPC_HD explicit LaneTab(int lane) {
     const int l = lane < 30 ? lane : 0;
     i = l / 6; j = l % 6;
@@ -124,7 +123,6 @@ struct LaneTab {
     s2[0] = 6 * l0 + j; s2[1] = 6 * l1 + j; s2[2] = 6 * l2 + j;
     s_m2j = 12 + j; s_m3j = 18 + j; s_m2i = 12 + i; s_m3i = 18 + i;
     const int r = lane < 5 ? lane : 0;
-    fscale = (r == 2 || r == 3) ? 1 : 0;
 #pragma unroll
     for (int t = 0; t < 5; ++t) fc[t] = (r == 2) ? (R_KK + t) : (r == 3) ? (R_KK + 6 + t) : e_off(r, t);
     fc0 = (r == 2) ? (R_KK + 5) : (r == 3) ? (R_KK + 11) : R_ZERO;
@@ -321,7 +319,7 @@ struct WarpSolver {
   // ---------------------------------------------------------------- phase A: stage KKT blocks (lane = stage)
   MPC_HD void linearize(const ProbState<T>& st) const {
     const int N = P.N;
-    const T dt = P.dt, mu = st.mu;
+    const T dt = P.dt, mu = st.mu, idt = T(1) / P.dt;
     for (int k = lane; k < N; k += 32) {
       T x0d[5], x1d[5], x1a[5];
 #pragma unroll
@@ -396,7 +394,7 @@ struct WarpSolver {
           Ru1 += rc(k, R_V + V_A_LO) * isl;
           ru1 -= mu * isl;
         }
-        rc(k, R_RU) = Ru0; rc(k, R_RU + 1) = Ru1; rc(k, R_RU + 2) = ru0; rc(k, R_RU + 3) = ru1;
+        rc(k, R_RU) = Ru0; rc(k, R_RU + 1) = Ru1; rc(k, R_RU + 2) = ru0 * idt; rc(k, R_RU + 3) = ru1 * idt;
       }
     }
     w.sync();
@@ -404,13 +402,20 @@ struct WarpSolver {
 
   // ---------------------------------------------------------------- phase C: backward Riccati sweep (lane = entry of [P | p])
   // Returns false (uniformly) if an exact-Hessian control block was not positive definite (caller retries with GN).
-  MPC_HD bool backward(int hess) const {
+  //
+  // Per stage, with M = [P|p] * [A d; 0 1], G = R~ + dt^2 P[2:4,2:4], J = -dt^2 G^-1 and mm = M[2:4, j] (+ ru/dt on the
+  // affine column):   T = J mm  ( = dt * [K | kff], stored as the gains ),   Pn = A^T M + M[2:4, i]^T T.
+  // The stage loop is software-pipelined by hand: the record loads of stage k-1 are issued between the shuffles of
+  // stage k and their consumers, so the LDS issue slots hide under the shuffle latency of the dependent chain.
+  struct BwdCoef { T h, c0, c1, c2, c3, c4, e0, e1, e2, Ru0, Ru1, rp0, rp1; };
+
+  template <int HESS>
+  MPC_HD bool backward_t() const {
     const int N = P.N;
     const T dt = P.dt, dt2 = dt * dt;
     T Pij = T(0);
     T lam[5] = {T(0), T(0), T(0), T(0), T(0)};
     const T ownf = (T)tb.own;
-    const T isj5 = ownf;
     bool ok = true;
     // per-lane record pointers, bumped one record per stage (one IADD each instead of index arithmetic per load)
     const int last = L.o_rec + REC_STRIDE * (N - 1);
@@ -418,43 +423,45 @@ struct WarpSolver {
     const T* pc0 = &sl[last + tb.c[0]]; const T* pc1 = &sl[last + tb.c[1]]; const T* pc2 = &sl[last + tb.c[2]];
     const T* pc3 = &sl[last + tb.c[3]]; const T* pc4 = &sl[last + tb.c[4]];
     const T* pe0 = &sl[last + tb.e[0]]; const T* pe1 = &sl[last + tb.e[1]]; const T* pe2 = &sl[last + tb.e[2]];
-    const T* pr = &sl[last];
+    const T* pr = &sl[last + R_RU];
     T* pk = &sl[last + R_KK + tb.j];
-    for (int k = N - 1; k >= 0; --k) {
-      const RecRef r{sl, L.o_rec + REC_STRIDE * k};
-      const T hterm = *ph;
-      const T c0 = *pc0, c1 = *pc1, c2 = *pc2, c3 = *pc3, c4 = *pc4;
-      const T e0 = *pe0, e1 = *pe1, e2 = *pe2;
-      const T Ru0 = pr[R_RU], Ru1 = pr[R_RU + 1], ru0 = pr[R_RU + 2], ru1 = pr[R_RU + 3];
-      T* const pkk = pk;
+    auto fetch = [&](BwdCoef& q) {
+      q.h = *ph; q.c0 = *pc0; q.c1 = *pc1; q.c2 = *pc2; q.c3 = *pc3; q.c4 = *pc4; q.e0 = *pe0; q.e1 = *pe1; q.e2 = *pe2;
+      q.Ru0 = pr[0]; q.Ru1 = pr[1]; q.rp0 = pr[2]; q.rp1 = pr[3];
       ph -= REC_STRIDE; pc0 -= REC_STRIDE; pc1 -= REC_STRIDE; pc2 -= REC_STRIDE; pc3 -= REC_STRIDE; pc4 -= REC_STRIDE;
-      pe0 -= REC_STRIDE; pe1 -= REC_STRIDE; pe2 -= REC_STRIDE; pr -= REC_STRIDE; pk -= REC_STRIDE;
-      Pij += hterm;                                   // x_{k+1} terms
+      pe0 -= REC_STRIDE; pe1 -= REC_STRIDE; pe2 -= REC_STRIDE; pr -= REC_STRIDE;
+    };
+    BwdCoef cur, nxt;
+    fetch(cur);
+    nxt = cur;
+    for (int k = N - 1; k >= 0; --k) {
+      Pij += cur.h;                                   // x_{k+1} terms
       // round 1: control block + M = [P|p] * Atilde
       const T p22 = w.shfl(Pij, 14), p23 = w.shfl(Pij, 15), p33 = w.shfl(Pij, 21);
       const T q0 = w.shfl(Pij, tb.s1[0]), q1 = w.shfl(Pij, tb.s1[1]), q2 = w.shfl(Pij, tb.s1[2]);
       const T q3 = w.shfl(Pij, tb.s1[3]), q4 = w.shfl(Pij, tb.s1[4]);
-      const T M = ownf * Pij + ((c0 * q0 + c1 * q1) + (c2 * q2 + c3 * q3) + c4 * q4);
-      const T G00 = Ru0 + dt2 * p22, G01 = dt2 * p23, G11 = Ru1 + dt2 * p33;
+      fetch(nxt);   // next stage's record, off the dependent chain (at k = 0 a harmless read of the state records below)
+      const T M = ownf * Pij + ((cur.c0 * q0 + cur.c1 * q1) + (cur.c2 * q2 + cur.c3 * q3) + cur.c4 * q4);
+      const T G00 = cur.Ru0 + dt2 * p22, G01 = dt2 * p23, G11 = cur.Ru1 + dt2 * p33;
       const T det = G00 * G11 - G01 * G01;
-      if (hess == HESS_EXACT) {
+      if (HESS == HESS_EXACT) {
         if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) { ok = false; break; }      // uniform across lanes
       }
-      T idet = m_rcp(det);
-      idet = idet * (T(2) - det * idet);              // one Newton step: the gains need the full precision
-      const T I00 = G11 * idet, I01 = -G01 * idet, I11 = G00 * idet;
-      // round 2: H = B^T M (+ ru on the affine column), Pn = A^T M - H^T G^-1 H
+      const T cdet = dt2 * m_rcp(det);
+      const T J00 = -cdet * G11, J01 = cdet * G01, J11 = -cdet * G00;
+      // round 2
       const T m2j = w.shfl(M, tb.s_m2j), m3j = w.shfl(M, tb.s_m3j);
       const T m2i = w.shfl(M, tb.s_m2i), m3i = w.shfl(M, tb.s_m3i);
       const T r0 = w.shfl(M, tb.s2[0]), r1 = w.shfl(M, tb.s2[1]), r2 = w.shfl(M, tb.s2[2]);
-      const T H0j = dt * m2j + isj5 * ru0, H1j = dt * m3j + isj5 * ru1;
-      const T K0j = -(I00 * H0j + I01 * H1j), K1j = -(I01 * H0j + I11 * H1j);
-      const T H0i = dt * m2i, H1i = dt * m3i;
-      T Pn = (M + e0 * r0) + (e1 * r1 + e2 * r2) + (H0i * K0j + H1i * K1j);
-      if (lane < 6) { pkk[0] = K0j; pkk[6] = K1j; }
-      if (hess == HESS_EXACT) {
+      const T mm2 = m2j + ownf * cur.rp0, mm3 = m3j + ownf * cur.rp1;
+      const T T0 = J00 * mm2 + J01 * mm3, T1 = J01 * mm2 + J11 * mm3;
+      T Pn = (M + cur.e0 * r0) + (cur.e1 * r1 + cur.e2 * r2) + (m2i * T0 + m3i * T1);
+      if (lane < 6) { pk[0] = T0; pk[6] = T1; }
+      pk -= REC_STRIDE;
+      if (HESS == HESS_EXACT) {
         // adjoint multipliers lam_{k+1} (every lane keeps the 5-vector), then
         // + dt * sum_i lam_{k+1,i} * hess f_i(x_k) on the (delta, v, psi) block of P_k
+        const RecRef r{sl, L.o_rec + REC_STRIDE * k};
 #pragma unroll
         for (int jj = 0; jj < 5; ++jj) lam[jj] += r[R_LC + jj];
         const T v = xa(k, 3);
@@ -474,30 +481,43 @@ struct WarpSolver {
         lam[2] = l2; lam[3] = l3; lam[4] = l4;
       }
       Pij = Pn;
+      cur = nxt;
     }
     w.sync();
     return ok;
   }
+  MPC_HD bool backward(int hess) const { return hess == HESS_EXACT ? backward_t<HESS_EXACT>() : backward_t<HESS_GN>(); }
 
   // ---------------------------------------------------------------- phase D: forward sweep (lane = state component)
+  // dx_{k+1} = A dx_k + B du_k + d_k with du_k = kff + K dx_k: lane r < 5 owns component r.  Rows 0, 1, 4 take their
+  // coefficients from A_k, rows 2, 3 from the stored gains dt*[K | kff]; the 5 new components are re-broadcast by
+  // shuffles.  Record loads are prefetched one stage ahead (off the dependent chain).
+  struct FwdCoef { T f0, f1, f2, f3, f4, fc, d; };
   MPC_HD void forward_sweep() const {
     const int N = P.N;
-    const T dt = P.dt;
-    const T scale = tb.fscale ? dt : T(1);
+    const T idt = T(1) / P.dt;
     const int row = lane < 5 ? lane : 0;
     T dx0 = T(0), dx1 = T(0), dx2 = T(0), dx3 = T(0), dx4 = T(0), mine = T(0);
     const T* pf0 = &sl[L.o_rec + tb.fc[0]]; const T* pf1 = &sl[L.o_rec + tb.fc[1]]; const T* pf2 = &sl[L.o_rec + tb.fc[2]];
     const T* pf3 = &sl[L.o_rec + tb.fc[3]]; const T* pf4 = &sl[L.o_rec + tb.fc[4]]; const T* pfc = &sl[L.o_rec + tb.fc0];
     T* pd = &sl[L.o_rec + row];
+    auto fetch = [&](FwdCoef& q) {
+      q.f0 = *pf0; q.f1 = *pf1; q.f2 = *pf2; q.f3 = *pf3; q.f4 = *pf4; q.fc = *pfc; q.d = pd[R_D];
+      pf0 += REC_STRIDE; pf1 += REC_STRIDE; pf2 += REC_STRIDE; pf3 += REC_STRIDE; pf4 += REC_STRIDE; pfc += REC_STRIDE;
+    };
+    FwdCoef cur, nxt;
+    fetch(cur);
+    nxt = cur;
     for (int k = 0; k < N; ++k) {
-      const T acc = *pfc + ((*pf0 * dx0 + *pf1 * dx1) + (*pf2 * dx2 + *pf3 * dx3) + *pf4 * dx4);
-      const T nx = mine + scale * acc + pd[R_D];
-      T* const pdd = pd;
-      pf0 += REC_STRIDE; pf1 += REC_STRIDE; pf2 += REC_STRIDE; pf3 += REC_STRIDE; pf4 += REC_STRIDE; pfc += REC_STRIDE; pd += REC_STRIDE;
+      const T acc = (cur.fc + cur.f0 * dx0) + (cur.f1 * dx1 + cur.f2 * dx2) + (cur.f3 * dx3 + cur.f4 * dx4);
+      const T nx = (mine + cur.d) + acc;
       dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);
       mine = nx;
-      if (lane < 5) pdd[R_DX] = nx;
-      if (lane == 2 || lane == 3) pdd[R_DU - 2] = acc;
+      if (lane < 5) pd[R_DX] = nx;
+      if (lane == 2 || lane == 3) pd[R_DU - 2] = acc * idt;
+      pd += REC_STRIDE;
+      fetch(nxt);   // at k = N-1 a harmless read just past the last record (still inside the CTA's shared memory)
+      cur = nxt;
     }
     w.sync();
   }

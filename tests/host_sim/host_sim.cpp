@@ -46,7 +46,7 @@ static void run(const mpcb200_config& cfg, const double* xref, double* Xio, doub
                 double* kkt, int B, int trace) {
   const int N = cfg.N;
   WLayout L(N);
-  std::vector<T> buf(L.words);
+  std::vector<T> buf(L.words + REC_STRIDE + 4);   // + one record: the forward sweep prefetches one record past the end
   HostWarp hw;
   for (int b = 0; b < B; ++b) {
     Job<T> J;
