@@ -431,10 +431,7 @@ struct WarpSolver {
       ph -= REC_STRIDE; pc0 -= REC_STRIDE; pc1 -= REC_STRIDE; pc2 -= REC_STRIDE; pc3 -= REC_STRIDE; pc4 -= REC_STRIDE;
       pe0 -= REC_STRIDE; pe1 -= REC_STRIDE; pe2 -= REC_STRIDE; pr -= REC_STRIDE;
     };
-    BwdCoef cur, nxt;
-    fetch(cur);
-    nxt = cur;
-    for (int k = N - 1; k >= 0; --k) {
+    auto stage = [&](int k, const BwdCoef& cur, BwdCoef& nxt) -> bool {
       Pij += cur.h;                                   // x_{k+1} terms
       // round 1: control block + M = [P|p] * Atilde
       const T p22 = w.shfl(Pij, 14), p23 = w.shfl(Pij, 15), p33 = w.shfl(Pij, 21);
@@ -445,7 +442,7 @@ struct WarpSolver {
       const T G00 = cur.Ru0 + dt2 * p22, G01 = dt2 * p23, G11 = cur.Ru1 + dt2 * p33;
       const T det = G00 * G11 - G01 * G01;
       if (HESS == HESS_EXACT) {
-        if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) { ok = false; break; }      // uniform across lanes
+        if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) return false;      // uniform across lanes
       }
       const T cdet = dt2 * m_rcp(det);
       const T J00 = -cdet * G11, J01 = cdet * G01, J11 = -cdet * G00;
@@ -481,8 +478,17 @@ struct WarpSolver {
         lam[2] = l2; lam[3] = l3; lam[4] = l4;
       }
       Pij = Pn;
-      cur = nxt;
+      return true;
+    };
+    // two stages per trip with ping-pong coefficient registers (no register moves between stages)
+    BwdCoef ca, cb;
+    fetch(ca);
+    int k = N - 1;
+    for (; k >= 1; k -= 2) {
+      if (!stage(k, ca, cb)) { ok = false; break; }
+      if (!stage(k - 1, cb, ca)) { ok = false; break; }
     }
+    if (ok && k == 0) ok = stage(0, ca, cb);
     w.sync();
     return ok;
   }
@@ -505,10 +511,7 @@ struct WarpSolver {
       q.f0 = *pf0; q.f1 = *pf1; q.f2 = *pf2; q.f3 = *pf3; q.f4 = *pf4; q.fc = *pfc; q.d = pd[R_D];
       pf0 += REC_STRIDE; pf1 += REC_STRIDE; pf2 += REC_STRIDE; pf3 += REC_STRIDE; pf4 += REC_STRIDE; pfc += REC_STRIDE;
     };
-    FwdCoef cur, nxt;
-    fetch(cur);
-    nxt = cur;
-    for (int k = 0; k < N; ++k) {
+    auto stage = [&](const FwdCoef& cur, FwdCoef& nxt) {
       const T acc = (cur.fc + cur.f0 * dx0) + (cur.f1 * dx1 + cur.f2 * dx2) + (cur.f3 * dx3 + cur.f4 * dx4);
       const T nx = (mine + cur.d) + acc;
       dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);
@@ -517,8 +520,12 @@ struct WarpSolver {
       if (lane == 2 || lane == 3) pd[R_DU - 2] = acc * idt;
       pd += REC_STRIDE;
       fetch(nxt);   // at k = N-1 a harmless read just past the last record (still inside the CTA's shared memory)
-      cur = nxt;
-    }
+    };
+    FwdCoef ca, cb;
+    fetch(ca);
+    int k = 0;
+    for (; k + 1 < N; k += 2) { stage(ca, cb); stage(cb, ca); }
+    if (k < N) stage(ca, cb);
     w.sync();
   }
 
@@ -731,7 +738,7 @@ struct WarpSolver {
   // ---------------------------------------------------------------- phase G: commit the step + complementarity statistics
   MPC_HD void commit(ProbState<T>& st, T al, T ad, T& avg, T& cmax) const {
     const int N = P.N;
-    const T mu = st.mu;
+    const T mu = st.mu, ikap = T(1) / P.kappa_sigma;
     T sum = T(0); cmax = T(0);
     for (int k = lane; k < N; k += 32) {
       const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
@@ -748,7 +755,10 @@ struct WarpSolver {
       auto upd = [&](int slot, T s, T ds, T snew) {
         const T nu = rc(k, R_V + slot);
         const T dnu = (mu - nu * s - nu * ds) * m_rcp(s);
-        const T nn = m_max(nu + ad * dnu, T(1e-30));
+        T nn = m_max(nu + ad * dnu, T(1e-30));
+        // keep the pair (s, nu) near the central path (IPOPT's kappa_sigma safeguard, eq. 16 of Waechter & Biegler 2006)
+        const T cen = mu * m_rcp(snew);
+        nn = m_min(m_max(nn, cen * ikap), cen * P.kappa_sigma);
         rc(k, R_V + slot) = nn;
         const T c = snew * nn; sum += c; cmax = m_max(cmax, c);
       };
