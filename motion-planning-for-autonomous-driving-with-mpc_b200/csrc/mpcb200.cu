@@ -339,6 +339,7 @@ __global__ void build_ref_window_kernel(int i, int Tlen, const double* path, con
 }
 
 // ===================================================================================================== handle
+#define MPCB200_HOST_STREAMS 4
 struct mpcb200_handle {
   mpcb200_config cfg;
   int wpc;              // warps (= problems) per CTA
@@ -355,6 +356,7 @@ struct mpcb200_handle {
   // host-path staging
   double *d_xref, *d_X, *d_U;
   int *d_status, *d_iters;
+  cudaStream_t hs[MPCB200_HOST_STREAMS];
   std::string err;
 };
 
@@ -371,8 +373,6 @@ static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
 template <typename T, int WPC>
 static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s) {
   const int ctas = (a.B + WPC - 1) / WPC;
-  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-  if (e != cudaSuccess) return e;
   mpc_warp_solve_kernel<T, WPC><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
   h->launches++;
   return cudaGetLastError();
@@ -380,8 +380,6 @@ static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaSt
 template <typename T, int WPC>
 static cudaError_t launch_loop(mpcb200_handle* h, const LoopArgs<T>& a, cudaStream_t s) {
   const int ctas = (a.B + WPC - 1) / WPC;
-  cudaError_t e = cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-  if (e != cudaSuccess) return e;
   mpc_warp_closed_loop_kernel<T, WPC><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
   h->launches++;
   return cudaGetLastError();
@@ -398,6 +396,20 @@ static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t
   if (h->wpc == 4) return launch_loop<T, 4>(h, a, s);
   if (h->wpc == 2) return launch_loop<T, 2>(h, a, s);
   return launch_loop<T, 1>(h, a, s);
+}
+
+// opt the handle's kernel instantiations in to their dynamic shared memory size (once, at create)
+template <typename T, int WPC>
+static cudaError_t configure_kernels_t(size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <typename T>
+static cudaError_t configure_kernels(const mpcb200_handle* h) {
+  if (h->wpc == 4) return configure_kernels_t<T, 4>(h->smem_bytes);
+  if (h->wpc == 2) return configure_kernels_t<T, 2>(h->smem_bytes);
+  return configure_kernels_t<T, 1>(h->smem_bytes);
 }
 
 static int ensure_stepwise_scratch(mpcb200_handle* h) {
@@ -465,6 +477,8 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
     if (need + reserve <= smem_max) { h->wpc = wpc; h->smem_bytes = need; break; }
   }
   if (!h->wpc) { g_create_err = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2; }
+  e = (cfg->precision == MPCB200_F64) ? configure_kernels<double>(h) : configure_kernels<float>(h);
+  if (e != cudaSuccess) { fail(nullptr, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e); delete h; return -1; }
   *out = h;
   return 0;
 }
@@ -472,6 +486,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
 void mpcb200_destroy(mpcb200_handle* h) {
   if (!h) return;
   cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift);
+  if (h->d_xref) for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) cudaStreamDestroy(h->hs[i]);
   cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);
   delete h;
 }
@@ -567,18 +582,27 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, dou
   if (!h->d_xref) {
     CK(cudaMalloc(&h->d_xref, mb * nx * 8)); CK(cudaMalloc(&h->d_X, mb * nx * 8)); CK(cudaMalloc(&h->d_U, mb * nu * 8));
     CK(cudaMalloc(&h->d_status, mb * 4)); CK(cudaMalloc(&h->d_iters, mb * 4));
+    for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
   }
-  cudaStream_t s = 0;
-  CK(cudaMemcpyAsync(h->d_xref, h_xref, B * nx * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(h->d_X, h_X, B * nx * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(h->d_U, h_U, B * nu * 8, cudaMemcpyHostToDevice, s));
-  int rc = mpcb200_solve(h, h->d_xref, h->d_X, h->d_U, h->d_status, h->d_iters, B, s);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h_X, h->d_X, B * nx * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h_U, h->d_U, B * nu * 8, cudaMemcpyDeviceToHost, s));
-  if (h_status) CK(cudaMemcpyAsync(h_status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-  if (h_iters) CK(cudaMemcpyAsync(h_iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  // Chunked pipeline over a few streams: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 run under the solve
+  // of chunk c (with pinned host buffers; pageable ones still work, the copies just serialise).  Chunks are even-sized
+  // so every CTA keeps a full 2-problem tile.
+  int nchunk = (B >= 512) ? MPCB200_HOST_STREAMS : 1;
+  int per = ((B + nchunk - 1) / nchunk + 1) & ~1;
+  for (int c = 0, lo = 0; lo < B; ++c, lo += per) {
+    const int n = (B - lo < per) ? (B - lo) : per;
+    cudaStream_t s = h->hs[c % MPCB200_HOST_STREAMS];
+    CK(cudaMemcpyAsync(h->d_xref + lo * nx, h_xref + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_X + lo * nx, h_X + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_U + lo * nu, h_U + lo * nu, n * nu * 8, cudaMemcpyHostToDevice, s));
+    int rc = mpcb200_solve(h, h->d_xref + lo * nx, h->d_X + lo * nx, h->d_U + lo * nu, h->d_status + lo, h->d_iters + lo, n, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_X + lo * nx, h->d_X + lo * nx, n * nx * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_U + lo * nu, h->d_U + lo * nu, n * nu * 8, cudaMemcpyDeviceToHost, s));
+    if (h_status) CK(cudaMemcpyAsync(h_status + lo, h->d_status + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (h_iters) CK(cudaMemcpyAsync(h_iters + lo, h->d_iters + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamSynchronize(h->hs[i]));
   return 0;
 }
 
