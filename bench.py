@@ -216,20 +216,19 @@ def run_product(args):
         total_ms = float(t.item())
     # ---- end-to-end through the public host-buffer API (pinned host memory, H2D + solve + D2H per step)
     hx = torch.as_tensor(xref).pin_memory(); hX0 = torch.as_tensor(X0).pin_memory(); hU0 = torch.as_tensor(U0).pin_memory()
-    hX, hU = hX0.clone().pin_memory(), hU0.clone().pin_memory()          # in/out buffers (warm start in, solution out)
-    for _ in range(2):
-        hX.copy_(hX0); hU.copy_(hU0)
-        opt.solve_batch_host(hx.numpy(), hX.numpy(), hU.numpy(), inplace=True)
+    hX, hU = torch.empty_like(hX0).pin_memory(), torch.empty_like(hU0).pin_memory()      # pinned result buffers
+    for _ in range(3):
+        opt.solve_batch_host(hx.numpy(), hX0.numpy(), hU0.numpy(), out=(hX.numpy(), hU.numpy()))
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
     n1 = h.launch_count
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        hX.copy_(hX0); hU.copy_(hU0)
-        Ue, Xe, ste, ite = opt.solve_batch_host(hx.numpy(), hX.numpy(), hU.numpy(), inplace=True)
+        Ue, Xe, ste, ite = opt.solve_batch_host(hx.numpy(), hX0.numpy(), hU0.numpy(), out=(hX.numpy(), hU.numpy()))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    assert (ste == 1).all() and float(Ue[0, 0, 1]) == float(Ue[0, 0, 1])               # the result was read back
     launches += h.launch_count - n1
     if dist:
         t = torch.tensor([e2e_s], device=dev, dtype=f64)

@@ -108,9 +108,11 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
                         double desired_velocity, const double* d_x0, double* d_traj, double* d_ctrl,
                         int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
-/* Host-buffer convenience used by the end-to-end path: H2D of xref/X/U, solve, D2H of X/U/status/iters, synchronous. */
-int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, double* h_U,
-                       int32_t* h_status, int32_t* h_iters, int32_t B);
+/* Host-buffer entry point (the end-to-end path): H2D of xref / X / U warm start, solve, D2H of the optimal X / U /
+ * status / iters, pipelined in chunks over internal streams; synchronous on return.  h_X_out / h_U_out may alias
+ * h_X / h_U (in place).  Host buffers should be pinned (pageable ones work but serialise the pipeline). */
+int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U,
+                       double* h_X_out, double* h_U_out, int32_t* h_status, int32_t* h_iters, int32_t B);
 
 /* Introspection for benches/tests. */
 int64_t mpcb200_launch_count(const mpcb200_handle* h);       /* kernels launched by this handle so far */

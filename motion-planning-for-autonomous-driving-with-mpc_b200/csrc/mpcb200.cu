@@ -357,6 +357,7 @@ struct mpcb200_handle {
   double *d_xref, *d_X, *d_U;
   int *d_status, *d_iters;
   cudaStream_t hs[MPCB200_HOST_STREAMS];
+  int* h_pin;           // pinned host staging for status + iters (a pageable D2H target would serialise the chunk pipeline)
   std::string err;
 };
 
@@ -462,7 +463,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   if (!h) { g_create_err = "out of host memory"; return -4; }
   h->cfg = *cfg;
   h->launches = 0; h->slab = h->state = h->obs_shift = nullptr;
-  h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr;
+  h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
   h->sw_xref = nullptr; h->sw_B = 0;
   const WLayout L(cfg->N);
   h->words = L.words;
@@ -487,6 +488,7 @@ void mpcb200_destroy(mpcb200_handle* h) {
   if (!h) return;
   cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift);
   if (h->d_xref) for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) cudaStreamDestroy(h->hs[i]);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);
   delete h;
 }
@@ -573,15 +575,18 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
   return 0;
 }
 
-int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, double* h_U, int32_t* h_status, int32_t* h_iters, int32_t B) {
+int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U, double* h_X_out, double* h_U_out,
+                       int32_t* h_status, int32_t* h_iters, int32_t B) {
   if (!h) return -2;
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  if (!h_xref || !h_X || !h_U || !h_X_out || !h_U_out) { h->err = "null host buffer"; return -2; }
   const int N = h->cfg.N;
   const size_t nx = (size_t)5 * (N + 1), nu = (size_t)2 * N, mb = h->cfg.max_batch;
   if (!h->d_xref) {
     CK(cudaMalloc(&h->d_xref, mb * nx * 8)); CK(cudaMalloc(&h->d_X, mb * nx * 8)); CK(cudaMalloc(&h->d_U, mb * nu * 8));
     CK(cudaMalloc(&h->d_status, mb * 4)); CK(cudaMalloc(&h->d_iters, mb * 4));
+    CK(cudaMallocHost(&h->h_pin, 2 * mb * 4));
     for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
   }
   // Chunked pipeline over a few streams: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 run under the solve
@@ -597,12 +602,14 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, double* h_X, dou
     CK(cudaMemcpyAsync(h->d_U + lo * nu, h_U + lo * nu, n * nu * 8, cudaMemcpyHostToDevice, s));
     int rc = mpcb200_solve(h, h->d_xref + lo * nx, h->d_X + lo * nx, h->d_U + lo * nu, h->d_status + lo, h->d_iters + lo, n, s);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_X + lo * nx, h->d_X + lo * nx, n * nx * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h_U + lo * nu, h->d_U + lo * nu, n * nu * 8, cudaMemcpyDeviceToHost, s));
-    if (h_status) CK(cudaMemcpyAsync(h_status + lo, h->d_status + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    if (h_iters) CK(cudaMemcpyAsync(h_iters + lo, h->d_iters + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_X_out + lo * nx, h->d_X + lo * nx, n * nx * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_U_out + lo * nu, h->d_U + lo * nu, n * nu * 8, cudaMemcpyDeviceToHost, s));
+    if (h_status) CK(cudaMemcpyAsync(h->h_pin + lo, h->d_status + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (h_iters) CK(cudaMemcpyAsync(h->h_pin + mb + lo, h->d_iters + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   }
   for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamSynchronize(h->hs[i]));
+  if (h_status) memcpy(h_status, h->h_pin, (size_t)B * 4);
+  if (h_iters) memcpy(h_iters, h->h_pin + mb, (size_t)B * 4);
   return 0;
 }
 

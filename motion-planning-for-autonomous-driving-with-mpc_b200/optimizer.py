@@ -225,22 +225,28 @@ class B200Optimizer(_Base):
         h.check(h.lib.mpcb200_sqp_end(h.h, X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), s))
         return U, X, status, iters
 
-    def solve_batch_host(self, xref, X_init, U_init, inplace=False):
+    def solve_batch_host(self, xref, X_init, U_init, inplace=False, out=None):
         """End-to-end call with HOST numpy buffers (H2D + solve + D2H inside the library, synchronous).
-        inplace=True: X_init/U_init (C-contiguous float64, ideally pinned) are overwritten with the solution."""
+        out=(X_out, U_out): C-contiguous float64 arrays (ideally pinned) that receive the solution;
+        inplace=True: X_init/U_init themselves are overwritten; otherwise fresh arrays are returned."""
         xref = np.ascontiguousarray(xref, np.float64)
-        if inplace:
-            X, U = X_init, U_init
-            assert X.flags.c_contiguous and U.flags.c_contiguous and X.dtype == np.float64 and U.dtype == np.float64
+        X_in = np.ascontiguousarray(X_init, np.float64)
+        U_in = np.ascontiguousarray(U_init, np.float64)
+        if out is not None:
+            X, U = out
+        elif inplace:
+            X, U = X_in, U_in
+            assert X is X_init and U is U_init, "inplace needs C-contiguous float64 arrays"
         else:
-            X = np.ascontiguousarray(X_init, np.float64).copy()
-            U = np.ascontiguousarray(U_init, np.float64).copy()
+            X, U = np.empty_like(X_in), np.empty_like(U_in)
+        assert X.flags.c_contiguous and U.flags.c_contiguous and X.dtype == np.float64 and U.dtype == np.float64
+        assert X.shape == X_in.shape and U.shape == U_in.shape
         B = xref.shape[0]
         status = np.empty(B, np.int32)
         iters = np.empty(B, np.int32)
         h = self.handle
-        h.check(h.lib.mpcb200_solve_host(h.h, xref.ctypes.data, X.ctypes.data, U.ctypes.data, status.ctypes.data,
-                                         iters.ctypes.data, B))
+        h.check(h.lib.mpcb200_solve_host(h.h, xref.ctypes.data, X_in.ctypes.data, U_in.ctypes.data, X.ctypes.data,
+                                         U.ctypes.data, status.ctypes.data, iters.ctypes.data, B))
         return U, X, status, iters
 
     def plant_step_shift(self, x, U, X):
