@@ -35,6 +35,7 @@ struct ParamsT {
   T r_sum, ego_off;
   T mu0, mu_min, mu_factor, tol_step, tol_feas, tau_min, bound_push;
   T acc_factor; int acc_iters;   // acceptable-level exit (warp core)
+  T mu_min_alpha;                // the barrier parameter is reduced only after a step of at least this length
   T kappa_sigma;                 // multipliers are kept within [mu/(kappa s), kappa mu/s] after every step
   int init_rollout;              // 1: initial states = Euler rollout of the initial controls from the pinned state
 };

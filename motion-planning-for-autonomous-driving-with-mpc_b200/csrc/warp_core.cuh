@@ -756,9 +756,9 @@ struct WarpSolver {
         const T nu = rc(k, R_V + slot);
         const T dnu = (mu - nu * s - nu * ds) * m_rcp(s);
         T nn = m_max(nu + ad * dnu, T(1e-30));
-        // keep the pair (s, nu) near the central path (IPOPT's kappa_sigma safeguard, eq. 16 of Waechter & Biegler 2006)
+        // lower safeguard on the multiplier, nu >= mu / (kappa_sigma s)  (IPOPT's kappa_sigma, Waechter & Biegler 2006 eq. 16)
         const T cen = mu * m_rcp(snew);
-        nn = m_min(m_max(nn, cen * ikap), cen * P.kappa_sigma);
+        nn = m_max(nn, cen * ikap);
         rc(k, R_V + slot) = nn;
         const T c = snew * nn; sum += c; cmax = m_max(cmax, c);
       };
@@ -849,7 +849,7 @@ struct WarpSolver {
       if (al * f.step_inf <= P.acc_factor * P.tol_step) { if (++st.nacc >= P.acc_iters) { st.status = ST_OPTIMAL; st.done = 1; return; } }
       else st.nacc = 0;
     }
-    if (al >= T(0.5)) {
+    if (al >= P.mu_min_alpha) {
       // monotone barrier update, linear (mu_factor) far out and superlinear (avg^1.5, as IPOPT's theta_mu) close in
       const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(P.mu_factor * avg, avg * m_sqrt(avg))));
       if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
