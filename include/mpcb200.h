@@ -62,6 +62,7 @@ typedef struct mpcb200_config {
   double tol_step, tol_feas;       /* convergence: inf-norm of the Newton step, l1 norm of the defects */
   double tau_min, bound_push;      /* fraction-to-the-boundary, initial interior push */
   double mu_min_alpha;             /* mu is reduced only after an accepted step length >= this */
+  double mu_up_alpha, mu_up_factor, mu_max;   /* barrier warm-up: mu *= mu_up_factor (<= mu_max) while the first steps are blocked below mu_up_alpha */
   double kappa_sigma;              /* multipliers kept within [mu/(kappa s), kappa mu/s] (IPOPT kappa_sigma) */
   double acc_factor;               /* acceptable exit: acc_iters consecutive steps <= acc_factor * tol_step at mu_min */
   int32_t acc_iters;

@@ -36,6 +36,7 @@ struct ParamsT {
   T mu0, mu_min, mu_factor, tol_step, tol_feas, tau_min, bound_push;
   T acc_factor; int acc_iters;   // acceptable-level exit (warp core)
   T mu_min_alpha;                // the barrier parameter is reduced only after a step of at least this length
+  T mu_up_alpha, mu_up_factor, mu_max;   // barrier warm-up: raise mu while the first steps are blocked below mu_up_alpha
   T kappa_sigma;                 // multipliers are kept within [mu/(kappa s), kappa mu/s] after every step
   int init_rollout;              // 1: initial states = Euler rollout of the initial controls from the pinned state
 };
@@ -47,7 +48,7 @@ struct ProbState {
   T a0_lo, a0_hi;     // stage-0 friction box (constants of the pinned stage)
   T kkt;              // last step inf-norm (diagnostic)
   T d_al, d_ap, d_ad, d_c1, d_dphi; int d_blk;   // diagnostics of the last iteration
-  int status, iters, done, nfail, nsoc, nacc;
+  int status, iters, done, nfail, nsoc, nacc, centered;
 };
 
 // ------------------------------------------------------------------ math wrappers

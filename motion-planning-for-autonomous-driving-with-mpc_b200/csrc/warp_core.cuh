@@ -248,7 +248,7 @@ struct WarpSolver {
   // trig cache.  Every lane ends with the same (uniform) ProbState.
   MPC_HD void init(ProbState<T>& st) const {
     const int N = P.N;
-    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.kkt = T(0);
+    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.kkt = T(0);
     st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
     const T de0 = xa(0, 2), v0 = xa(0, 3);
     const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
@@ -848,6 +848,21 @@ struct WarpSolver {
       // floor is convergence, not progress
       if (al * f.step_inf <= P.acc_factor * P.tol_step) { if (++st.nacc >= P.acc_iters) { st.status = ST_OPTIMAL; st.done = 1; return; } }
       else st.nacc = 0;
+    }
+    // Barrier warm-up: while no step of length >= 0.5 has been taken, a step blocked hard by the fraction-to-the-boundary
+    // rule (alpha < mu_up_alpha) means the barrier is invisible next to the cost gradient -- the iteration would crawl
+    // one bound per step.  Raise mu (and the multipliers with it, keeping s*nu on the central path) instead.
+    if (!st.centered) {
+      if (al >= T(0.5)) st.centered = 1;
+      else if (al < P.mu_up_alpha && st.mu * P.mu_up_factor <= P.mu_max) {
+        st.mu *= P.mu_up_factor;
+        for (int k = lane; k < P.N; k += 32) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) rc(k, R_V + j) *= P.mu_up_factor;
+        }
+        w.sync();
+        return;
+      }
     }
     if (al >= P.mu_min_alpha) {
       // monotone barrier update, linear (mu_factor) far out and superlinear (avg^1.5, as IPOPT's theta_mu) close in
