@@ -10,7 +10,8 @@
  * `h_` pointer is a HOST pointer.  All calls are asynchronous on the given CUDA stream unless stated.  Return value:
  * 0 on success, negative on an API / CUDA error (text via mpcb200_last_error).  Per-problem solver outcome goes to
  * `d_status[B]` using the Forcespro exit codes the reference already knows (test/FORCESNLPsolver/include/
- * FORCESNLPsolver.h:70-106): 1 optimal, 0 iteration limit, -6 NaN, -7 no progress; additionally -8 = the pinned
+ * FORCESNLPsolver.h:70-106): 1 optimal, 0 iteration limit, -6 NaN, -7 no progress; additionally 3 = feasible but stalled
+ * at the rounding-noise floor of the arithmetic (usable, accuracy below tol_step) and -8 = the pinned
  * stage X_0 violates a constraint (IPOPT would report an infeasible problem).  The batch is never aborted
  * (contrast optimizer.py:330).
  *
@@ -66,6 +67,8 @@ typedef struct mpcb200_config {
   double kappa_sigma;              /* multipliers kept within [mu/(kappa s), kappa mu/s] (IPOPT kappa_sigma) */
   double acc_factor;               /* acceptable exit: acc_iters consecutive steps <= acc_factor * tol_step at mu_min */
   int32_t acc_iters;
+  int32_t stall_iters;             /* status 3 after this many iterations at mu_min without halving the step (noise floor) */
+  int32_t reserved0;
   int32_t init_rollout;            /* 1: initial states = Euler rollout of the initial controls from X_0 (X warm start ignored) */
 } mpcb200_config;
 

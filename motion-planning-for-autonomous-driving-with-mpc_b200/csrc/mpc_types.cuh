@@ -16,6 +16,7 @@ namespace mpcb200 {
 enum : int {
   ST_OPTIMAL = 1,        // converged
   ST_MAXIT = 0,          // iteration limit
+  ST_STALLED = 3,        // feasible, at mu_min, step stalled at the rounding-noise floor above tol_step (usable, less accurate)
   ST_NAN = -6,           // NaN/Inf met
   ST_NOPROGRESS = -7,    // line search failed repeatedly
   ST_INFEASIBLE_X0 = -8, // pinned stage violates a constraint (friction row infeasible / nonconvex, x0 inside obstacle)
@@ -35,6 +36,7 @@ struct ParamsT {
   T r_sum, ego_off;
   T mu0, mu_min, mu_factor, tol_step, tol_feas, tau_min, bound_push;
   T acc_factor; int acc_iters;   // acceptable-level exit (warp core)
+  int stall_iters;               // stall exit after this many iterations at mu_min without halving the step
   T mu_min_alpha;                // the barrier parameter is reduced only after a step of at least this length
   T mu_up_alpha, mu_up_factor, mu_max;   // barrier warm-up: raise mu while the first steps are blocked below mu_up_alpha
   T kappa_sigma;                 // multipliers are kept within [mu/(kappa s), kappa mu/s] after every step
@@ -48,7 +50,8 @@ struct ProbState {
   T a0_lo, a0_hi;     // stage-0 friction box (constants of the pinned stage)
   T kkt;              // last step inf-norm (diagnostic)
   T d_al, d_ap, d_ad, d_c1, d_dphi; int d_blk;   // diagnostics of the last iteration
-  int status, iters, done, nfail, nsoc, nacc, centered;
+  T best;             // smallest accepted step length*norm seen at mu_min (stall detection)
+  int status, iters, done, nfail, nsoc, nacc, centered, nstall;
 };
 
 // ------------------------------------------------------------------ math wrappers

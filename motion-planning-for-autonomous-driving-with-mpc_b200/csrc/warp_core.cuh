@@ -248,7 +248,7 @@ struct WarpSolver {
   // trig cache.  Every lane ends with the same (uniform) ProbState.
   MPC_HD void init(ProbState<T>& st) const {
     const int N = P.N;
-    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.kkt = T(0);
+    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.nstall = 0; st.best = T(1e30); st.kkt = T(0);
     st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
     const T de0 = xa(0, 2), v0 = xa(0, 3);
     const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
@@ -848,6 +848,11 @@ struct WarpSolver {
       // floor is convergence, not progress
       if (al * f.step_inf <= P.acc_factor * P.tol_step) { if (++st.nacc >= P.acc_iters) { st.status = ST_OPTIMAL; st.done = 1; return; } }
       else st.nacc = 0;
+      // stall exit: the step no longer halves -- the iterate sits at the rounding-noise floor of the arithmetic
+      // (fp32 with barrier weights ~1/mu_min on an active obstacle row).  Usable, flagged ST_STALLED.
+      const T sz = al * f.step_inf;
+      if (sz < T(0.5) * st.best) { st.best = sz; st.nstall = 0; }
+      else if (++st.nstall >= P.stall_iters) { st.status = ST_STALLED; st.done = 1; return; }
     }
     // Barrier warm-up: while no step of length >= 0.5 has been taken, a step blocked hard by the fraction-to-the-boundary
     // rule (alpha < mu_up_alpha) means the barrier is invisible next to the cost gradient -- the iteration would crawl
