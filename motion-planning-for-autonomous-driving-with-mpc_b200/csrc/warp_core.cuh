@@ -809,6 +809,8 @@ struct WarpSolver {
       if (need > st.rho) st.rho = need * T(1.5) + T(1);
     }
     const T slope = f.dphi - st.rho * f.c1;
+    const T cfloor = T(8) * epsm * f.mag;                       // rounding-noise floor of the l1 infeasibility
+    const bool trust = (f.c1 <= cfloor) && (f.step_inf <= P.trust_step);
     T al = f.a_p;
     bool accepted = false;
     for (int t = 0; t < P.ls_max; ++t) {
@@ -817,7 +819,15 @@ struct WarpSolver {
       bool ok = trial_merit(st, al, false, dphi, c1, nz);
       T dm = dphi + st.rho * (c1 - f.c1);
       T noise = T(8) * epsm * (nz + st.rho * f.mag);
+#if defined(MPC_DEBUG_LS) && !defined(__CUDACC__)
+      if (lane == 0) printf("      ls t=%d al=%.3e ok=%d dphi=%.4e c1=%.4e (c1_0 %.4e) dm=%.4e thresh=%.4e noise=%.3e nz=%.3e mag=%.3e slope=%.3e\n", t, (double)al, (int)ok,
+             (double)dphi, (double)c1, (double)f.c1, (double)dm, (double)(T(1e-4) * al * slope + noise), (double)noise, (double)nz, (double)f.mag, (double)slope);
+#endif
       if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; break; }
+      // Newton-trust acceptance: feasible to working precision and a short step.  There the l1 merit cannot judge the
+      // step any more -- defect rounding noise times the (large, unknown) dynamics multipliers exceeds the predicted
+      // change -- while the undamped Newton iteration converges quadratically; stalls are caught by the stall exit.
+      if (trust && ok && m_finite(dm) && c1 <= T(2) * cfloor) { accepted = true; break; }
       if (t == 0 && ok && m_finite(dm)) {
         trial_points_reshoot(al);
         ok = trial_merit(st, al, true, dphi, c1, nz);
