@@ -88,6 +88,11 @@ const char* mpcb200_last_error(const mpcb200_handle* h);   /* h may be NULL: err
 int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U,
                   int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
+/* Same solve from the reference's step-0 initial guess (X_0 tiled, zero controls, optimizer.py:578-583): d_X / d_U are
+ * outputs only, nothing but d_xref is read. */
+int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U,
+                       int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
+
 /* Same solve, one kernel launch per SQP iteration with the per-problem KKT slab (iterate, multipliers, slacks,
  * Riccati blocks) staged HBM -> shared memory by TMA bulk copy and written back each launch:
  *   begin: load problem data, initialise;  iter: `n_iter` iterations per call;  end: write X, U, status, iters. */
@@ -116,7 +121,7 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
 
 /* Host-buffer entry point (the end-to-end path): H2D of xref / X / U warm start, solve, D2H of the optimal X / U /
  * status / iters, pipelined in chunks over internal streams; synchronous on return.  h_X_out / h_U_out may alias
- * h_X / h_U (in place).  Host buffers should be pinned (pageable ones work but serialise the pipeline). */
+ * h_X / h_U (in place).  h_X = h_U = NULL: cold start (X_0 tiled, zero controls), only xref is uploaded.  Host buffers should be pinned (pageable ones work but serialise the pipeline). */
 int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U,
                        double* h_X_out, double* h_U_out, int32_t* h_status, int32_t* h_iters, int32_t B);
 

@@ -44,6 +44,7 @@ EXPORTS = {
                                            C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_solve_cold": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_void_p]),
     "mpcb200_solve_host": (C.c_int, [C.c_void_p] * 8 + [C.c_int32]),
     "mpcb200_launch_count": (C.c_int64, [C.c_void_p]),
     "mpcb200_workspace_words": (C.c_int32, [C.c_void_p]),

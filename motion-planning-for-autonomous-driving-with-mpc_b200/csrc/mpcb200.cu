@@ -75,6 +75,7 @@ struct SolveArgs {
   int B;
   int mode;
   int n_iter;
+  int cold;             // 1: X / U are outputs only (cold start: X_0 tiled, zero controls)
 };
 
 // shared-memory carve-up of one CTA: [WPC slabs of T][float64 staging: xref | X | U for WPC problems]
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const __grid_c
   WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   const bool need_xref = (a.mode != MODE_ITER);
-  const bool need_warm = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
+  const bool need_init = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
+  const bool need_warm = need_init && !a.cold;
 
   // ---- problem data in: xref (+ warm start) of the CTA's tile, HBM -> staging
   if (need_xref) {
@@ -156,8 +158,8 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const __grid_c
     }
   }
 
-  if (need_warm) {
-    if (valid) { S.load(sm.xref(wid), sm.X(wid), sm.U(wid), a.obstacle, obs); S.init(st); }
+  if (need_init) {
+    if (valid) { S.load(sm.xref(wid), need_warm ? sm.X(wid) : nullptr, need_warm ? sm.U(wid) : nullptr, a.obstacle, obs); S.init(st); }
     else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
   } else {
     // resume: the slab image comes back by one TMA bulk copy per warp, the per-problem scalars by plain loads
@@ -424,7 +426,7 @@ static int ensure_stepwise_scratch(mpcb200_handle* h) {
 
 template <typename T>
 static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref, double* X, double* U, int* status, int* iters,
-                    int B, cudaStream_t s) {
+                    int B, cudaStream_t s, int cold = 0) {
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
   if (mode != MODE_ONESHOT) { int rc = ensure_stepwise_scratch(h); if (rc) return rc; }
@@ -433,7 +435,7 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
   a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
   a.slab = (T*)h->slab; a.state = (ProbState<T>*)h->state; a.obs_shift = (T*)h->obs_shift;
-  a.B = B; a.mode = mode; a.n_iter = n_iter;
+  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold;
   cudaError_t e = dispatch_solve<T>(h, a, s);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel launch", e);
   return 0;
@@ -499,6 +501,14 @@ int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* 
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
   return do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
+}
+
+int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters,
+                       int32_t B, void* stream) {
+  if (!h) return -2;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
+  return do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
 }
 
 int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X, const double* d_U, int32_t B, void* stream) {
@@ -580,7 +590,8 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
   if (!h) return -2;
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
-  if (!h_xref || !h_X || !h_U || !h_X_out || !h_U_out) { h->err = "null host buffer"; return -2; }
+  if (!h_xref || !h_X_out || !h_U_out || (!h_X != !h_U)) { h->err = "null host buffer"; return -2; }
+  const bool cold = !h_X;                               // no warm start: nothing but xref is uploaded
   const int N = h->cfg.N;
   const size_t nx = (size_t)5 * (N + 1), nu = (size_t)2 * N, mb = h->cfg.max_batch;
   if (!h->d_xref) {
@@ -598,9 +609,12 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
     const int n = (B - lo < per) ? (B - lo) : per;
     cudaStream_t s = h->hs[c % MPCB200_HOST_STREAMS];
     CK(cudaMemcpyAsync(h->d_xref + lo * nx, h_xref + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_X + lo * nx, h_X + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_U + lo * nu, h_U + lo * nu, n * nu * 8, cudaMemcpyHostToDevice, s));
-    int rc = mpcb200_solve(h, h->d_xref + lo * nx, h->d_X + lo * nx, h->d_U + lo * nu, h->d_status + lo, h->d_iters + lo, n, s);
+    if (!cold) {
+      CK(cudaMemcpyAsync(h->d_X + lo * nx, h_X + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(h->d_U + lo * nu, h_U + lo * nu, n * nu * 8, cudaMemcpyHostToDevice, s));
+    }
+    int rc = cold ? mpcb200_solve_cold(h, h->d_xref + lo * nx, h->d_X + lo * nx, h->d_U + lo * nu, h->d_status + lo, h->d_iters + lo, n, s)
+                  : mpcb200_solve(h, h->d_xref + lo * nx, h->d_X + lo * nx, h->d_U + lo * nu, h->d_status + lo, h->d_iters + lo, n, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h_X_out + lo * nx, h->d_X + lo * nx, n * nx * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h_U_out + lo * nu, h->d_U + lo * nu, n * nu * 8, cudaMemcpyDeviceToHost, s));

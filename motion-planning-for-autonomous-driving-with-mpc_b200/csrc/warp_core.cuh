@@ -195,21 +195,22 @@ struct WarpSolver {
   }
 
   // ---------------------------------------------------------------- problem I/O (float64 row-major arrays of ONE problem)
-  // xref [N+1][5] (row 0 = pinned state), Xin [N+1][5], Uin [N][2].  Differences are formed in float64, then rounded.
+  // xref [N+1][5] (row 0 = pinned state), Xin [N+1][5], Uin [N][2] (either may be null: cold start = the reference's
+  // step-0 guess, X_0 tiled and zero controls, optimizer.py:578-583).  Differences are formed in float64, then rounded.
   MPC_HD void load(const double* xref, const double* Xin, const double* Uin, const double* obstacle_abs, T* obs_out) const {
     const int N = P.N;
     const double ox = xref[0], oy = xref[1];
     for (int j = 0; j < 3; ++j) { obs_out[2 * j] = (T)(obstacle_abs[2 * j] - ox); obs_out[2 * j + 1] = (T)(obstacle_abs[2 * j + 1] - oy); }
     for (int k = lane; k <= N; k += 32) {
       const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
-      const double* xin = (k == 0) ? xref : (Xin + 5 * k);           // stage 0 is pinned to X_ref[:,0]
+      const double* xin = (k == 0 || !Xin) ? xref : (Xin + 5 * k);   // stage 0 is pinned to X_ref[:,0]; no warm start = X_0 tiled
       sx(k, S_XR + 0) = (T)(rho[0] - ox); sx(k, S_XR + 1) = (T)(rho[1] - oy);
       sx(k, S_XR + 2) = (T)rho[2]; sx(k, S_XR + 3) = (T)rho[3]; sx(k, S_XR + 4) = (T)rho[4];
       for (int j = 0; j < 5; ++j) sx(k, S_XT + j) = (T)(xin[j] - rho[j]);
       if (k < N) {
         const double* rho1 = xref + 5 * ((k + 2 < N) ? (k + 2) : N);
         rc(k, R_CP) = (T)(rho[0] - rho1[0]); rc(k, R_CP + 1) = (T)(rho[1] - rho1[1]);
-        rc(k, R_U) = (T)Uin[2 * k]; rc(k, R_U + 1) = (T)Uin[2 * k + 1];
+        rc(k, R_U) = Uin ? (T)Uin[2 * k] : T(0); rc(k, R_U + 1) = Uin ? (T)Uin[2 * k + 1] : T(0);
         rc(k, R_ZERO) = T(0); rc(k, R_ONE) = T(1);
       }
     }
@@ -220,7 +221,7 @@ struct WarpSolver {
       double x[5];
       for (int j = 0; j < 5; ++j) x[j] = xref[j];
       for (int k = 0; k < N; ++k) {
-        const double u0 = Uin[2 * k], u1 = Uin[2 * k + 1];
+        const double u0 = Uin ? Uin[2 * k] : 0.0, u1 = Uin ? Uin[2 * k + 1] : 0.0;
         const double v = x[3], sn = sin(x[4]), cs = cos(x[4]), tn = tan(x[2]);
         x[0] += (double)P.dt * v * cs; x[1] += (double)P.dt * v * sn; x[2] += (double)P.dt * u0; x[3] += (double)P.dt * u1;
         x[4] += (double)P.dt * v * tn / (double)P.l_wb;

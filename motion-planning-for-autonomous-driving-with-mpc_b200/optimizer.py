@@ -199,13 +199,18 @@ class B200Optimizer(_Base):
         xref = self._dev(xref)
         B = xref.shape[0]
         assert xref.shape[1:] == (self.N + 1, 5), xref.shape
-        X = (xref[:, :1, :].expand(B, self.N + 1, 5).contiguous() if X_init is None else self._dev(X_init).clone())
-        U = (t.zeros(B, self.N, 2, dtype=t.float64, device=self.device) if U_init is None else self._dev(U_init).clone())
+        cold = X_init is None and U_init is None
+        if cold:
+            X = t.empty(B, self.N + 1, 5, dtype=t.float64, device=self.device)
+            U = t.empty(B, self.N, 2, dtype=t.float64, device=self.device)
+        else:
+            X = (xref[:, :1, :].expand(B, self.N + 1, 5).contiguous() if X_init is None else self._dev(X_init).clone())
+            U = (t.zeros(B, self.N, 2, dtype=t.float64, device=self.device) if U_init is None else self._dev(U_init).clone())
         status = t.empty(B, dtype=t.int32, device=self.device)
         iters = t.empty(B, dtype=t.int32, device=self.device)
         h = self.handle
-        h.check(h.lib.mpcb200_solve(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(),
-                                    iters.data_ptr(), B, self._stream()))
+        fn = h.lib.mpcb200_solve_cold if cold else h.lib.mpcb200_solve
+        h.check(fn(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), B, self._stream()))
         return U, X, status, iters
 
     def solve_batch_stepwise(self, xref, X_init=None, U_init=None, n_iter=None):
@@ -225,28 +230,35 @@ class B200Optimizer(_Base):
         h.check(h.lib.mpcb200_sqp_end(h.h, X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), s))
         return U, X, status, iters
 
-    def solve_batch_host(self, xref, X_init, U_init, inplace=False, out=None):
+    def solve_batch_host(self, xref, X_init=None, U_init=None, inplace=False, out=None):
         """End-to-end call with HOST numpy buffers (H2D + solve + D2H inside the library, synchronous).
+        X_init = U_init = None: cold start (the reference's step-0 guess), only xref is uploaded.
         out=(X_out, U_out): C-contiguous float64 arrays (ideally pinned) that receive the solution;
         inplace=True: X_init/U_init themselves are overwritten; otherwise fresh arrays are returned."""
         xref = np.ascontiguousarray(xref, np.float64)
-        X_in = np.ascontiguousarray(X_init, np.float64)
-        U_in = np.ascontiguousarray(U_init, np.float64)
-        if out is not None:
-            X, U = out
-        elif inplace:
-            X, U = X_in, U_in
-            assert X is X_init and U is U_init, "inplace needs C-contiguous float64 arrays"
-        else:
-            X, U = np.empty_like(X_in), np.empty_like(U_in)
-        assert X.flags.c_contiguous and U.flags.c_contiguous and X.dtype == np.float64 and U.dtype == np.float64
-        assert X.shape == X_in.shape and U.shape == U_in.shape
         B = xref.shape[0]
+        cold = X_init is None and U_init is None
+        if cold:
+            X_in = U_in = None
+            X, U = out if out is not None else (np.empty((B, self.N + 1, 5)), np.empty((B, self.N, 2)))
+        else:
+            X_in = np.ascontiguousarray(X_init, np.float64)
+            U_in = np.ascontiguousarray(U_init, np.float64)
+            if out is not None:
+                X, U = out
+            elif inplace:
+                X, U = X_in, U_in
+                assert X is X_init and U is U_init, "inplace needs C-contiguous float64 arrays"
+            else:
+                X, U = np.empty_like(X_in), np.empty_like(U_in)
+        assert X.flags.c_contiguous and U.flags.c_contiguous and X.dtype == np.float64 and U.dtype == np.float64
+        assert X.shape == (B, self.N + 1, 5) and U.shape == (B, self.N, 2)
         status = np.empty(B, np.int32)
         iters = np.empty(B, np.int32)
         h = self.handle
-        h.check(h.lib.mpcb200_solve_host(h.h, xref.ctypes.data, X_in.ctypes.data, U_in.ctypes.data, X.ctypes.data,
-                                         U.ctypes.data, status.ctypes.data, iters.ctypes.data, B))
+        h.check(h.lib.mpcb200_solve_host(h.h, xref.ctypes.data, X_in.ctypes.data if not cold else None,
+                                         U_in.ctypes.data if not cold else None, X.ctypes.data, U.ctypes.data,
+                                         status.ctypes.data, iters.ctypes.data, B))
         return U, X, status, iters
 
     def plant_step_shift(self, x, U, X):

@@ -191,3 +191,59 @@ def test_closed_loop_on_device_matches_oracle_closed_loop():
     sc, opt32 = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=32)
     t32, c32, st32, _ = opt32.optimize_batch(x0[:1])
     assert np.abs(t32[0] - traj_o).max() < 5e-3 and np.abs(c32[0] - u_o).max() < 5e-3
+
+
+def test_cold_start_entry_points_equal_explicit_warm_start():
+    """mpcb200_solve_cold / host path without X, U == the same solve with the reference's step-0 guess passed explicitly."""
+    import mpc_b200
+    N, B = 30, 130
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=256)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 5)
+    Ua, Xa, sta, ita = _np(*opt.solve_batch(xref, X0, U0))
+    Ub, Xb, stb, itb = _np(*opt.solve_batch(xref))
+    assert np.array_equal(Ua, Ub) and np.array_equal(Xa, Xb) and np.array_equal(sta, stb) and np.array_equal(ita, itb)
+    Xo, Uo = np.full_like(X0, np.nan), np.full_like(U0, np.nan)
+    Uc, Xc, stc, itc = opt.solve_batch_host(xref, out=(Xo, Uo))
+    assert Xc is Xo and Uc is Uo and np.array_equal(Ua, Uo) and np.array_equal(Xa, Xo) and np.array_equal(sta, stc)
+    Ud, Xd, std_, itd = opt.solve_batch_host(xref, X0, U0)          # warm-start upload path, fresh outputs
+    assert np.array_equal(Ua, Ud) and np.array_equal(Xa, Xd) and np.array_equal(X0[:, 1:], np.repeat(xref[:, :1], N, axis=1))
+
+
+@pytest.mark.parametrize("name", ["ZAM_Over-1_1_LFfile", "USA_Peach-2_1_T-1", "ZAM_Tutorial-1_2_T-1", "ZAM_Tutorial_Urban-3_2",
+                                  "USA_Lanker-2_18_T-1_LF"])
+def test_all_scenarios_converge_and_match_live_oracle(name):
+    """Config 5 scenarios (N = 30, random initial states): every instance converges; live oracle on a sample."""
+    import mpc_b200
+    from oracle import nlp, ipm
+    N, B = 30, 512
+    sc, opt = _opt(name, N, "f32", max_batch=B, max_iter=200)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 20261020)
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert (st == 1).mean() > 0.995 and np.isin(st, (1, 3)).all(), np.unique(st, return_counts=True)
+    xn = nlp.euler_step(X[:, :-1], U, sc.dt)
+    assert np.abs(xn - X[:, 1:]).max() < 5e-4
+    n = 0
+    for b in (0, 100, 511):
+        d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+        r = ipm.solve(d, nlp.pack(U0[b], X0[b]))
+        if r["status"] != 1 or st[b] != 1:
+            continue                                   # the oracle's own IPM is less robust than the device solver
+        Uo, Xo = nlp.split(r["w"], N)
+        assert np.abs(U[b] - Uo).max() < 1e-3 and np.abs(X[b] - Xo).max() < 1e-3
+        n += 1
+    assert n >= 1
+
+
+def test_rollout_start_and_exact_hessian_on_device():
+    import mpc_b200
+    N, B = 50, 64
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("USA_Lanker-2_18_T-1_LF", B, N, 20261019)
+    sc, opt = _opt("USA_Lanker-2_18_T-1_LF", N, "f64", "gn", max_batch=B)
+    Ua, Xa, sta, _ = _np(*opt.solve_batch(xref))
+    sc, opt_r = _opt("USA_Lanker-2_18_T-1_LF", N, "f64", "gn", max_batch=B, init_rollout=1)
+    Ub, Xb, stb, _ = _np(*opt_r.solve_batch(xref, np.full_like(X0, 1e3), U0))     # X warm start ignored
+    sc, opt_e = _opt("USA_Lanker-2_18_T-1_LF", N, "f64", "exact", max_batch=B)
+    Uc, Xc, stc, _ = _np(*opt_e.solve_batch(xref))
+    ok = (sta == 1) & (stb == 1) & (stc == 1)
+    assert ok.mean() > 0.95
+    assert np.abs(Ua[ok] - Ub[ok]).max() < 1e-5 and np.abs(Ua[ok] - Uc[ok]).max() < 1e-5
