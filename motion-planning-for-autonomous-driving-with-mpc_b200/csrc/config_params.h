@@ -34,7 +34,7 @@ inline void default_config(mpcb200_config* c, int N, int precision) {
   c->r_sum = 1.2; c->ego_offset = 0.75;                                    // lane following: dummy obstacle (Q11)
   const double ob[6] = {-100.0, 0.0, -100.0, 0.0, -100.0, 0.0};
   for (int i = 0; i < 6; ++i) c->obstacle[i] = ob[i];
-  c->mu0 = 0.1; c->mu_factor = 0.2; c->tau_min = 0.99; c->bound_push = 1e-2;
+  c->mu0 = 0.01; c->mu_factor = 0.2; c->tau_min = 0.99; c->bound_push = 1e-2;
   if (precision == MPCB200_F64) { c->mu_min = 1e-9; c->tol_step = 1e-8; c->tol_feas = 1e-8; c->acc_factor = 1000.0; }
   else                          { c->mu_min = 1e-6; c->tol_step = 2e-5; c->tol_feas = 1e-4; c->acc_factor = 5.0; }
   c->acc_iters = 4; c->stall_iters = 10; c->trust_step = 1e-2; c->init_rollout = 0; c->kappa_sigma = 1e10; c->mu_min_alpha = 0.5;
