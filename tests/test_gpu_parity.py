@@ -12,7 +12,7 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 TOL = {"f32": 1e-3, "f64": 1e-6}
 
 
-def _opt(name, N, precision="f32", hessian="exact", max_batch=4096, **kw):
+def _opt(name, N, precision="f32", hessian="gn", max_batch=4096, **kw):
     import torch
     import mpc_b200
     from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
