@@ -341,6 +341,15 @@ class B200Optimizer(_Base):
         return traj_s, np.array(u_c), np.array(t_v)
 
 
+    def save_results(self, save_path, states, controls, solve_time):
+        """Writes `planned states.txt`, `control inputs.txt`, `solve time.txt`, `deviation.txt`, `RMSD.txt` in the format
+        MPCPlanner.plot_* writes them (mpc_planner.py:190-290), so a run diffs against the reference's recorded fixtures."""
+        from . import results
+        origin = getattr(self.configuration, "origin_reference_path", None)
+        return results.write_result_files(save_path, states, controls, solve_time,
+                                          np.asarray(self.resampled_path_points, float), origin)
+
+
 def make_configuration(scenario, predict_horizon=None, framework_name="casadi", noised=False):
     """A `PlanningConfiguration`-shaped object (configuration.py:106-336) built from mpc_b200.scenarios data, for use
     where commonroad is not installed.  Only the fields Optimizer reads are populated."""

@@ -247,3 +247,19 @@ def test_rollout_start_and_exact_hessian_on_device():
     ok = (sta == 1) & (stb == 1) & (stc == 1)
     assert ok.mean() > 0.95
     assert np.abs(Ua[ok] - Ub[ok]).max() < 1e-5 and np.abs(Ua[ok] - Uc[ok]).max() < 1e-5
+
+
+def test_reference_contract_run_writes_result_files_in_the_recorded_bands(tmp_path):
+    """optimize() (N = 10, noise-free) -> the five txt files of the reference; bands of the recorded noisy run and of
+    the noise-free oracle replay: step-0 braking at the friction limit, end speed 17.41 m/s, RMSD_x ~ 0.24 m."""
+    from mpc_b200 import results
+    g = np.load(os.path.join(G, "recorded_runs.npz"))
+    sc, opt = _opt("ZAM_Over-1_1_LF", 10, "f64", max_batch=8)
+    x, u, t = opt.optimize()
+    out = opt.save_results(str(tmp_path / "run"), x, u, t)
+    back = results.read_result_files(str(tmp_path / "run"))
+    assert back["planned states.txt"].shape == g["casadi_zam_lf_x"].shape and back["control inputs.txt"].shape == g["casadi_zam_lf_u"].shape
+    assert np.array_equal(back["planned states.txt"][0], g["casadi_zam_lf_x"][0])              # same initial state as the recorded run
+    assert abs(u[0, 1] + np.sqrt(11.5)) < 1e-6 and abs(x[-1, 3] - 17.41) < 0.05
+    assert abs(out["RMSD.txt"][0] - 0.24) < 0.03 and abs(out["RMSD.txt"][0] - g["casadi_zam_lf_rmsd"][0]) < 0.05
+    assert (t > 0).all() and t.shape == (30,)
