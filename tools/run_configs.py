@@ -96,6 +96,25 @@ def main():
                         max_abs_err_traj_vs_oracle=float(np.abs(ts - traj_o).max()), max_abs_err_ctrl_vs_oracle=float(np.abs(us - u_o).max()),
                         end_speed=float(ts[-1, 3])))
         print(json.dumps(out[-1]), flush=True)
+        # ---- config 1b: the same closed loop for 1024 perturbed egos, whole loop on the device (one launch)
+        sc, x0b, *_ = mpc_b200.make_batch("ZAM_Over-1_1_LF", 1024, N, 20261017)
+        opt32 = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision="f32", max_batch=1024, device=local)
+        d_x0 = opt32._dev(x0b)
+        for _ in range(2):
+            tr, ct, stl, itl = opt32.optimize_batch(d_x0, return_device=True)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
+        for _ in range(5):
+            tr, ct, stl, itl = opt32.optimize_batch(d_x0, return_device=True)
+        e1.record(torch.cuda.current_stream(dev)); torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        stl, itl = stl.cpu().numpy(), itl.cpu().numpy()
+        out.append(dict(config="1b", scenario="ZAM_Over-1_1_LF", B=1024, N=N, closed_loop_steps=int(stl.shape[1]), ms_per_batch=ms,
+                        closed_loops_per_s=1024 / (ms * 1e-3), mpc_steps_per_s=1024 * stl.shape[1] / (ms * 1e-3),
+                        converged_steps=f"{int(np.isin(stl, (1, 3)).sum())}/{stl.size}", mean_sqp_iters_per_step=float(itl.mean()),
+                        mean_sqp_iters_warm_steps=float(itl[:, 1:].mean())))
+        print(json.dumps(out[-1]), flush=True)
     if dist:
         dist.barrier()
     for cfg_id, (name, B, N, seed, kw) in {2: ("ZAM_Over-1_1_LF", 1024, 30, 20261017, {}),
