@@ -105,7 +105,7 @@ __device__ __forceinline__ bool tile_is_bulk(int nvalid, int per_problem) {
 // One warp per ego instance; WPC warps (problems) per CTA.  All SQP iterations of a problem run inside the launch
 // (MODE_ONESHOT), or `n_iter` of them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
 template <typename T, int WPC>
-__global__ void __launch_bounds__(32 * WPC) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
+__global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   __shared__ __align__(8) uint64_t bar_io;
   __shared__ __align__(8) uint64_t bar_w[WPC];

@@ -665,13 +665,18 @@ struct WarpSolver {
     dphi = T(0); c1 = T(0); nz = T(0);
     bool ok = true;
     T lg = T(0), lga = T(0);
-    auto lrow = [&](T num, T den) {
-      const T rt = num * m_rcp(den);
-      ok = ok && (rt > T(-1));
-      const T l = m_log1p(m_max(rt, T(-0.999999)));
-      lg += l; lga += m_abs(l);
-    };
-    for (int k = lane; k < N; k += 32) {
+    // The barrier terms -mu*log(s_new/s_old) = -mu*log1p(rt) of the 11-12 rows are gathered first; when EVERY ratio of
+    // the warp's stages is small (the usual case once the iterate is close) the logs are a 4-term series instead of 12
+    // log1pf calls -- a warp-uniform choice, so no divergence.
+    for (int k0 = 0; k0 < N; k0 += 32) {
+      const int k = k0 + lane;
+      const bool act = k < N;
+      T rts[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rts[i] = T(0);
+      if (act) {
+      int nr = 0;
+      auto lrow = [&](T num, T den) { rts[nr++] = num * m_rcp(den); };
       const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
       const T du0 = al * rc(k, R_DU), du1 = al * rc(k, R_DU + 1);
       const T nu0 = u0 + du0, nu1 = u1 + du1;
@@ -710,7 +715,6 @@ struct WarpSolver {
       lrow(-du0, m_slack(P.dd_max - u0));
       const T ahi = (k == 0) ? st.a0_hi : P.a_max;
       lrow(-du1, m_slack(ahi - u1));
-      if (k == 0) lrow(du1, m_slack(u1 - st.a0_lo));
       lrow(dxb[2], m_slack(x1a[2] - P.de_min));
       lrow(-dxb[2], m_slack(P.de_max - x1a[2]));
       lrow(dxb[3], m_slack(x1a[3] - P.v_min));
@@ -727,6 +731,25 @@ struct WarpSolver {
         lrow(ds, s);
         T hb, g1, g2, g3; obst(j, xba[0], xba[1], snb, csb, hb, g1, g2, g3);
         c1 += m_resid((hb - P.r_sum) - (s + ds), hb);
+      }
+      if (k == 0) lrow(du1, m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side (slot 11)
+      }   // act
+      bool small = true;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { small = small && (m_abs(rts[i]) < T(0.02)); ok = ok && (rts[i] > T(-1)); }
+      if (sizeof(T) == 4 && w.all(small)) {      // float only: the series is good to ~3e-8 relative
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const T x = rts[i];
+          const T l = x * (T(1) + x * (T(-0.5) + x * (T(1) / T(3) - T(0.25) * x)));     // log1p(x), |x| < 0.02: rel. error < x^4/5 = 3e-8
+          lg += l; lga += m_abs(l);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const T l = m_log1p(m_max(rts[i], T(-0.999999)));
+          lg += l; lga += m_abs(l);
+        }
       }
     }
     dphi -= mu * lg;
