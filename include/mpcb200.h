@@ -65,6 +65,7 @@ typedef struct mpcb200_config {
   double mu_min_alpha;             /* mu is reduced only after an accepted step length >= this */
   double mu_up_alpha, mu_up_factor, mu_max;   /* barrier warm-up: mu *= mu_up_factor (<= mu_max) while the first steps are blocked below mu_up_alpha */
   double kappa_sigma;              /* multipliers kept within [mu/(kappa s), kappa mu/s] (IPOPT kappa_sigma) */
+  double screen_inv_curv;          /* obstacle rows whose barrier curvature mu/s^2 is below 1/this are skipped for the iteration (<= 0: keep all) */
   double trust_step;               /* feasible iterate + step below this: the Newton step is accepted without the merit test */
   double acc_factor;               /* acceptable exit: acc_iters consecutive steps <= acc_factor * tol_step at mu_min */
   int32_t acc_iters;

@@ -36,6 +36,7 @@ struct ParamsT {
   T r_sum, ego_off;
   T mu0, mu_min, mu_factor, tol_step, tol_feas, tau_min, bound_push;
   T acc_factor; int acc_iters;   // acceptable-level exit (warp core)
+  T screen_inv_curv;             // obstacle rows with mu/s^2 < 1/screen_inv_curv are screened out for the iteration (0: never)
   T trust_step;                  // Newton-trust acceptance (no merit test) for feasible iterates and steps below this
   int stall_iters;               // stall exit after this many iterations at mu_min without halving the step
   T mu_min_alpha;                // the barrier parameter is reduced only after a step of at least this length

@@ -46,6 +46,7 @@ enum : int {
   R_KK = 53,    // 12 gains times dt: dt*(K0[0..4] k0 K1[0..4] k1)
   R_DX = 65,    // 5  step dx_{k+1}
   R_DU = 70,    // 2  step du_k
+  R_FAR = 72,   // 1  obstacle rows of x_{k+1} screened out this iteration (1) or live (0)
   REC_STRIDE = 73
 };
 // state record k = 0..N
@@ -182,6 +183,23 @@ struct WarpSolver {
     h = d2 * ih;
     gx = dx * ih; gy = dy * ih;
     gp = o * (gy * cs - gx * sn);
+  }
+
+  // Row screening.  An obstacle row whose slack s = distance - r_sum is so large that its barrier curvature mu/s^2 is
+  // below `screen_curv` contributes less than rounding error to the KKT system (lane following: dummy obstacle 130 m away,
+  // quirk Q11).  Such rows are skipped for the iteration (decided once in linearize(), stored in R_FAR); their slack and
+  // multiplier stay frozen and they count with s*nu = mu in the complementarity average.  Conservative test on the centre
+  // distance: every circle pair is at least (centre distance - obs_spread - ego_off) apart.
+  MPC_HD T far_threshold2(T mu) const {
+    if (!(P.screen_inv_curv > T(0))) return T(3e38);       // screening off
+    const T sp1 = m_sqrt((obs[2] - obs[0]) * (obs[2] - obs[0]) + (obs[3] - obs[1]) * (obs[3] - obs[1]));
+    const T sp2 = m_sqrt((obs[4] - obs[0]) * (obs[4] - obs[0]) + (obs[5] - obs[1]) * (obs[5] - obs[1]));
+    const T reach = P.r_sum + P.ego_off + m_max(sp1, sp2) + m_sqrt(mu * P.screen_inv_curv);
+    return reach * reach;
+  }
+  MPC_HD bool is_far(T px, T py, T thr2) const {
+    const T dx = px - obs[0], dy = py - obs[1];
+    return dx * dx + dy * dy > thr2;
   }
 
   // defect of stage k: d = xt_k - xt_{k+1} + dt*f(x_k,u_k) + (rho_k - rho_{k+1})      (optimizer.py:380-382, Euler)
@@ -321,6 +339,7 @@ struct WarpSolver {
   MPC_HD void linearize(const ProbState<T>& st) const {
     const int N = P.N;
     const T dt = P.dt, mu = st.mu, idt = T(1) / P.dt;
+    const T thr2 = far_threshold2(mu);
     for (int k = lane; k < N; k += 32) {
       T x0d[5], x1d[5], x1a[5];
 #pragma unroll
@@ -362,6 +381,9 @@ struct WarpSolver {
         lc[3] += -vlo + vhi;
       }
       T h01 = T(0), h04 = T(0), h14 = T(0);
+      const bool far = is_far(x1a[0], x1a[1], thr2);
+      rc(k, R_FAR) = far ? T(1) : T(0);
+      if (!far) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         T h, gx, gy, gp; obst(j, x1a[0], x1a[1], t1.sn, t1.cs, h, gx, gy, gp);
@@ -376,6 +398,7 @@ struct WarpSolver {
         hd[1] += wgt * gy * gy; h14 += wgt * gy * gp; hd[4] += wgt * gp * gp;
         g[0] += cg * gx; g[1] += cg * gy; g[4] += cg * gp;
         lc[0] -= nu * gx; lc[1] -= nu * gy; lc[4] -= nu * gp;
+      }
       }
       rc(k, R_H + H00) = hd[0]; rc(k, R_H + H01) = h01; rc(k, R_H + H04) = h04; rc(k, R_H + H11) = hd[1];
       rc(k, R_H + H14) = h14; rc(k, R_H + H44) = hd[4]; rc(k, R_H + H22) = hd[2]; rc(k, R_H + H33) = hd[3];
@@ -582,6 +605,7 @@ struct WarpSolver {
       row_limits(m_slack(x1a[3] - P.v_min), rc(k, R_V + V_V_LO), nx[3], mu, tau, o);
       row_limits(m_slack(P.v_max - x1a[3]), rc(k, R_V + V_V_HI), -nx[3], mu, tau, o);
       const T sn1 = sx(k + 1, S_TR), cs1 = sx(k + 1, S_TR + 1);
+      if (rc(k, R_FAR) == T(0)) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         T h, gx, gy, gp; obst(j, x1a[0], x1a[1], sn1, cs1, h, gx, gy, gp);
@@ -590,6 +614,7 @@ struct WarpSolver {
         const T ds = gx * nx[0] + gy * nx[1] + gp * nx[4] + r;
         o.c1 += m_resid(r, h);
         row_limits(s, rc(k, R_V + V_OB0 + j), ds, mu, tau, o);
+      }
       }
 #pragma unroll
       for (int j = 0; j < 5; ++j) o.step_inf = m_max(o.step_inf, m_abs(nx[j]));
@@ -722,17 +747,19 @@ struct WarpSolver {
       // obstacle rows: the slack moves with its own Newton step ds (from the OLD linearisation)
       const T sn0 = sx(k + 1, S_TR), cs0 = sx(k + 1, S_TR + 1);
       const T snb = sx(k + 1, S_TRT), csb = sx(k + 1, S_TRT + 1);
+      if (rc(k, R_FAR) == T(0)) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         T h, gx, gy, gp; obst(j, x1a[0], x1a[1], sn0, cs0, h, gx, gy, gp);
         const T s = rc(k, R_S + j);
         const T r = (h - P.r_sum) - s;
         const T ds = al * (gx * rc(k, R_DX) + gy * rc(k, R_DX + 1) + gp * rc(k, R_DX + 4) + r);
-        lrow(ds, s);
+        rts[7 + j] = ds * m_rcp(s);
         T hb, g1, g2, g3; obst(j, xba[0], xba[1], snb, csb, hb, g1, g2, g3);
         c1 += m_resid((hb - P.r_sum) - (s + ds), hb);
       }
-      if (k == 0) lrow(du1, m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side (slot 11)
+      }
+      if (k == 0) rts[10] = du1 * m_rcp(m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side
       }   // act
       bool small = true;
 #pragma unroll
@@ -796,6 +823,7 @@ struct WarpSolver {
       upd(V_V_LO, m_slack(x1a[3] - P.v_min), dx[3], m_slack(nvv - P.v_min));
       upd(V_V_HI, m_slack(P.v_max - x1a[3]), -dx[3], m_slack(P.v_max - nvv));
       const T sn1 = sx(k + 1, S_TR), cs1 = sx(k + 1, S_TR + 1);
+      if (rc(k, R_FAR) == T(0)) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         T h, gx, gy, gp; obst(j, x1a[0], x1a[1], sn1, cs1, h, gx, gy, gp);
@@ -805,6 +833,9 @@ struct WarpSolver {
         const T snew = m_slack(s + al * ds);
         upd(V_OB0 + j, s, ds, snew);
         rc(k, R_S + j) = snew;
+      }
+      } else {
+        sum += T(3) * mu;                          // screened rows sit on the central path: s*nu = mu
       }
       rc(k, R_U) = nu0; rc(k, R_U + 1) = nu1;
 #pragma unroll
