@@ -603,7 +603,8 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
   // Chunked pipeline over a few streams: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 run under the solve
   // of chunk c (with pinned host buffers; pageable ones still work, the copies just serialise).  Chunks are even-sized
   // so every CTA keeps a full 2-problem tile.
-  int nchunk = (B >= 512) ? MPCB200_HOST_STREAMS : 1;
+  int nchunk = (B >= 4096) ? MPCB200_HOST_STREAMS : (B >= 512 ? 2 : 1);   // small batches are latency-bound: fewer, larger chunks
+  if (const char* ev = getenv("MPCB200_HOST_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= MPCB200_HOST_STREAMS) nchunk = v; }   // tuning knob
   int per = ((B + nchunk - 1) / nchunk + 1) & ~1;
   for (int c = 0, lo = 0; lo < B; ++c, lo += per) {
     const int n = (B - lo < per) ? (B - lo) : per;
