@@ -76,6 +76,7 @@ struct SolveArgs {
   int mode;
   int n_iter;
   int cold;             // 1: X / U are outputs only (cold start: X_0 tiled, zero controls)
+  int refine;           // 1: second pass -- only instances whose status is not 1 are solved (warm start = their X / U)
 };
 
 // shared-memory carve-up of one CTA: [WPC slabs of T][float64 staging: xref | X | U for WPC problems]
@@ -158,8 +159,11 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(cons
     }
   }
 
+  // refinement pass: a problem that already converged keeps its result (its staging rows are written back untouched)
+  const bool skip = a.refine && valid && a.status[b] == ST_OPTIMAL;
   if (need_init) {
-    if (valid) { S.load(sm.xref(wid), need_warm ? sm.X(wid) : nullptr, need_warm ? sm.U(wid) : nullptr, a.obstacle, obs); S.init(st); }
+    if (skip) { st.done = 1; st.status = ST_OPTIMAL; st.iters = a.iters ? a.iters[b] : 0; }
+    else if (valid) { S.load(sm.xref(wid), need_warm ? sm.X(wid) : nullptr, need_warm ? sm.U(wid) : nullptr, a.obstacle, obs); S.init(st); }
     else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
   } else {
     // resume: the slab image comes back by one TMA bulk copy per warp, the per-problem scalars by plain loads
@@ -176,17 +180,17 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(cons
     } else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
   }
 
-  if (a.mode != MODE_END && valid) {
+  if (a.mode != MODE_END && valid && !skip) {
     for (int it = 0; it < a.n_iter && !st.done; ++it) S.iterate(st);
   }
 
   if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
     // solution back to float64 row-major (rho is added back in float64), staging -> HBM
-    if (valid) {
+    if (valid && !skip) {
       S.store(sm.xref(wid), sm.X(wid), sm.U(wid));
       if (lane == 0) {
         if (a.status) a.status[b] = st.status;
-        if (a.iters) a.iters[b] = st.iters;
+        if (a.iters) a.iters[b] = st.iters + (a.refine && a.iters ? a.iters[b] : 0);
       }
     }
     if (tile_is_bulk<WPC>(nvalid, nx) && tile_is_bulk<WPC>(nvalid, nu)) {
@@ -346,6 +350,8 @@ struct mpcb200_handle {
   mpcb200_config cfg;
   int wpc;              // warps (= problems) per CTA
   size_t smem_bytes;
+  int wpc64;            // same for the float64 refinement pass of a float32 handle (cfg.refine_f64)
+  size_t smem64;
   int words;            // slab words per problem
   void* slab;           // global slab image [max_batch][words] (stepwise mode), allocated on first use
   void* state;
@@ -374,9 +380,9 @@ static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
 
 template <typename T, int WPC>
-static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s) {
+static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s, size_t smem) {
   const int ctas = (a.B + WPC - 1) / WPC;
-  mpc_warp_solve_kernel<T, WPC><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
+  mpc_warp_solve_kernel<T, WPC><<<ctas, 32 * WPC, smem, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
@@ -389,10 +395,10 @@ static cudaError_t launch_loop(mpcb200_handle* h, const LoopArgs<T>& a, cudaStre
 }
 
 template <typename T>
-static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s) {
-  if (h->wpc == 4) return launch_solve<T, 4>(h, a, s);
-  if (h->wpc == 2) return launch_solve<T, 2>(h, a, s);
-  return launch_solve<T, 1>(h, a, s);
+static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s, int wpc, size_t smem) {
+  if (wpc == 4) return launch_solve<T, 4>(h, a, s, smem);
+  if (wpc == 2) return launch_solve<T, 2>(h, a, s, smem);
+  return launch_solve<T, 1>(h, a, s, smem);
 }
 template <typename T>
 static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t s) {
@@ -409,10 +415,10 @@ static cudaError_t configure_kernels_t(size_t smem) {
   return cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <typename T>
-static cudaError_t configure_kernels(const mpcb200_handle* h) {
-  if (h->wpc == 4) return configure_kernels_t<T, 4>(h->smem_bytes);
-  if (h->wpc == 2) return configure_kernels_t<T, 2>(h->smem_bytes);
-  return configure_kernels_t<T, 1>(h->smem_bytes);
+static cudaError_t configure_kernels(int wpc, size_t smem) {
+  if (wpc == 4) return configure_kernels_t<T, 4>(smem);
+  if (wpc == 2) return configure_kernels_t<T, 2>(smem);
+  return configure_kernels_t<T, 1>(smem);
 }
 
 static int ensure_stepwise_scratch(mpcb200_handle* h) {
@@ -435,9 +441,24 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
   a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
   a.slab = (T*)h->slab; a.state = (ProbState<T>*)h->state; a.obs_shift = (T*)h->obs_shift;
-  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold;
-  cudaError_t e = dispatch_solve<T>(h, a, s);
+  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold; a.refine = 0;
+  cudaError_t e = dispatch_solve<T>(h, a, s, h->wpc, h->smem_bytes);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel launch", e);
+  return 0;
+}
+
+// second pass of a float32 handle with cfg.refine_f64: float64 arithmetic (float32 tolerances) on the instances that did
+// not reach status 1, warm-started from their float32 result
+static int refine_pass(mpcb200_handle* h, const double* xref, double* X, double* U, int* status, int* iters, int B, cudaStream_t s) {
+  if (!status) { h->err = "refine_f64 needs a status buffer"; return -2; }
+  SolveArgs<double> a;
+  a.P = params_from_config<double>(h->cfg);
+  for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
+  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
+  a.slab = nullptr; a.state = nullptr; a.obs_shift = nullptr;
+  a.B = B; a.mode = MODE_ONESHOT; a.n_iter = h->cfg.max_iter; a.cold = 0; a.refine = 1;
+  cudaError_t e = dispatch_solve<double>(h, a, s, h->wpc64, h->smem64);
+  if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel<double> (refinement) launch", e);
   return 0;
 }
 
@@ -480,8 +501,18 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
     if (need + reserve <= smem_max) { h->wpc = wpc; h->smem_bytes = need; break; }
   }
   if (!h->wpc) { g_create_err = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2; }
-  e = (cfg->precision == MPCB200_F64) ? configure_kernels<double>(h) : configure_kernels<float>(h);
+  e = (cfg->precision == MPCB200_F64) ? configure_kernels<double>(h->wpc, h->smem_bytes) : configure_kernels<float>(h->wpc, h->smem_bytes);
   if (e != cudaSuccess) { fail(nullptr, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e); delete h; return -1; }
+  h->wpc64 = 0; h->smem64 = 0;
+  if (cfg->precision == MPCB200_F32 && cfg->refine_f64) {
+    for (int wpc : {2, 1}) {
+      const size_t need = smem_bytes_for(cfg->N, L.words, 8, wpc);
+      if (need + reserve <= smem_max) { h->wpc64 = wpc; h->smem64 = need; break; }
+    }
+    if (!h->wpc64) { g_create_err = "horizon too long for the float64 refinement pass"; delete h; return -2; }
+    e = configure_kernels<double>(h->wpc64, h->smem64);
+    if (e != cudaSuccess) { fail(nullptr, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e); delete h; return -1; }
+  }
   *out = h;
   return 0;
 }
@@ -500,7 +531,9 @@ int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* 
   if (!h) return -2;
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
-  return do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
+  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
+  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, d_xref, d_X, d_U, d_status, d_iters, B, s);
+  return rc;
 }
 
 int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters,
@@ -508,7 +541,9 @@ int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, dou
   if (!h) return -2;
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
-  return do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
+  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
+  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, d_xref, d_X, d_U, d_status, d_iters, B, s);
+  return rc;
 }
 
 int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X, const double* d_U, int32_t B, void* stream) {

@@ -263,3 +263,26 @@ def test_reference_contract_run_writes_result_files_in_the_recorded_bands(tmp_pa
     assert abs(u[0, 1] + np.sqrt(11.5)) < 1e-6 and abs(x[-1, 3] - 17.41) < 0.05
     assert abs(out["RMSD.txt"][0] - 0.24) < 0.03 and abs(out["RMSD.txt"][0] - g["casadi_zam_lf_rmsd"][0]) < 0.05
     assert (t > 0).all() and t.shape == (30,)
+
+
+def test_float64_refinement_pass_converges_the_stalled_collision_avoidance_instances():
+    """cfg.refine_f64: instances the fp32 arithmetic leaves at its rounding floor (status 3) are re-solved in float64
+    arithmetic by a second launch; converged instances are untouched (bit-identical)."""
+    import mpc_b200
+    from oracle import nlp, ipm
+    N, B = 30, 256
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_CA", B, N, 20261018)
+    sc, opt = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300)
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    sc, optr = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300, refine_f64=1)
+    Ur, Xr, str_, itr = _np(*optr.solve_batch(xref))
+    assert optr.handle.launch_count == 2
+    same = st == 1
+    assert same.any() and (~same).any()                                     # the sample has stalled instances
+    assert np.array_equal(U[same], Ur[same]) and np.array_equal(X[same], Xr[same]) and np.array_equal(it[same], itr[same])
+    assert (str_ == 1).mean() > 0.99 and (itr[~same] > it[~same]).all()
+    for b in [int(i) for i in np.where(~same & (str_ == 1))[0][:3]]:
+        d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+        w = nlp.pack(Ur[b], Xr[b])
+        r = ipm.solve(d, w)
+        assert r["status"] == 1 and np.abs(r["w"] - w).max() < 1e-4          # was ~3e-3 before the refinement
