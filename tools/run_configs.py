@@ -118,14 +118,14 @@ def main():
     if dist:
         dist.barrier()
     for cfg_id, (name, B, N, seed, kw) in {2: ("ZAM_Over-1_1_LF", 1024, 30, 20261017, {}),
-                                           3: ("ZAM_Over-1_1_CA", 4096, 30, 20261018, dict(max_iter=300)),
+                                           3: ("ZAM_Over-1_1_CA", 4096, 30, 20261018, dict(max_iter=300, refine_f64=1)),
                                            4: ("USA_Lanker-2_18_T-1_LF", 8192, 50, 20261019, {})}.items():
         r = timed_solve(name, B, N, seed, **kw); r["config"] = cfg_id
         if rank == 0:
             print(json.dumps(r), flush=True)
     tot_ms, rows = 0.0, []
     for i, name in enumerate(SCEN6):
-        r = timed_solve(name, 4096, 30, 20261020 + i, max_iter=300, n_check=2); rows.append(r); tot_ms += r["ms_per_batch"]
+        r = timed_solve(name, 4096, 30, 20261020 + i, max_iter=300, n_check=2, **(dict(refine_f64=1) if name.endswith("_CA") else {})); rows.append(r); tot_ms += r["ms_per_batch"]
     if rank == 0:
         print(json.dumps(dict(config=5, gpus=world, total_instances=6 * 4096, ms_total=tot_ms, solves_per_s=6 * 4096 / (tot_ms * 1e-3),
                               per_scenario=rows)), flush=True)
