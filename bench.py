@@ -73,7 +73,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_sample = max(cores, min(BATCH, 4 * cores))
+    n_sample = max(cores, min(BATCH, 16 * cores))          # bounded sample per step (~0.5 s on all cores)
     import mpc_b200
     sc, x0, xref, X, U = mpc_b200.make_batch(SCENARIO, n_sample, N_HORIZON, SEED)
     jobs = [(SCENARIO, N_HORIZON, xref[b], X[b], U[b]) for b in range(n_sample)]
@@ -260,7 +260,7 @@ def run_product(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_sample = max(cores, min(BATCH, 16 * cores))
+        n_sample = BATCH                                   # the whole workload: ~25 ms per solve per core, 10-40 core-seconds
         rate, dt, ok = cpu_oracle_rate(n_sample, cores)
         cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                "sample": f"first {n_sample} of the {BATCH} instances, float64 oracle (oracle/ipm.py), Pool({cores}), {dt:.1f} s, {ok} converged"}
