@@ -71,8 +71,6 @@ typedef struct mpcb200_config {
   int32_t acc_iters;
   int32_t stall_iters;             /* status 3 after this many iterations at mu_min without halving the step (noise floor) */
   int32_t refine_f64;              /* precision F32 only: re-solve instances that did not reach status 1 in float64 arithmetic (second launch) */
-  int32_t team_max_batch;          /* batches up to this size run a 2-warp team per problem (latency-bound regime); 0: never */
-  int32_t reserved0;
   int32_t init_rollout;            /* 1: initial states = Euler rollout of the initial controls from X_0 (X warm start ignored) */
 } mpcb200_config;
 

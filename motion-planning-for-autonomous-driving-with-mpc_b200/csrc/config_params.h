@@ -37,7 +37,7 @@ inline void default_config(mpcb200_config* c, int N, int precision) {
   c->mu0 = 0.01; c->mu_factor = 0.2; c->tau_min = 0.99; c->bound_push = 1e-2;
   if (precision == MPCB200_F64) { c->mu_min = 1e-9; c->tol_step = 1e-8; c->tol_feas = 1e-8; c->acc_factor = 1000.0; }
   else                          { c->mu_min = 1e-6; c->tol_step = 2e-5; c->tol_feas = 1e-4; c->acc_factor = 5.0; }
-  c->acc_iters = 4; c->stall_iters = 10; c->refine_f64 = 0; c->team_max_batch = 1024; c->reserved0 = 0; c->trust_step = 1e-2; c->screen_inv_curv = 1e6; c->init_rollout = 0; c->kappa_sigma = 1e10; c->mu_min_alpha = 0.5;
+  c->acc_iters = 4; c->stall_iters = 10; c->refine_f64 = 0; c->trust_step = 1e-2; c->screen_inv_curv = 1e6; c->init_rollout = 0; c->kappa_sigma = 1e10; c->mu_min_alpha = 0.5;
   c->mu_up_alpha = 0.5; c->mu_up_factor = 10.0; c->mu_max = 1e3;
 }
 

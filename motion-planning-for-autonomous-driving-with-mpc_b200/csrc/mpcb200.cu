@@ -105,14 +105,12 @@ __device__ __forceinline__ bool tile_is_bulk(int nvalid, int per_problem) {
 // ===================================================================================================== solve kernel
 // One warp per ego instance; WPC warps (problems) per CTA.  All SQP iterations of a problem run inside the launch
 // (MODE_ONESHOT), or `n_iter` of them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
-template <typename T, int WPC, int TEAM>
-__global__ void __launch_bounds__(32 * WPC * TEAM, 16 / (WPC * TEAM)) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
+template <typename T, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   __shared__ __align__(8) uint64_t bar_io;
   __shared__ __align__(8) uint64_t bar_w[WPC];
-  // TEAM warps per problem: warp (wid, part) of problem `wid` of this CTA
-  const int wid = (threadIdx.x >> 5) / TEAM, part = (threadIdx.x >> 5) % TEAM, lane = threadIdx.x & 31;
-  constexpr int NTHR = 32 * WPC * TEAM;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
   const WLayout L(N);
   const Smem<T, WPC> sm(smem_raw, N, L.words);
@@ -130,9 +128,9 @@ __global__ void __launch_bounds__(32 * WPC * TEAM, 16 / (WPC * TEAM)) mpc_warp_s
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  const WarpCtx w(TEAM == 2 ? 1 + wid : 0);
+  const WarpCtx w;
   T obs[6];
-  WarpSolver<T, TEAM> S(a.P, SlabRef<T>{wid * L.words}, obs, w, part);
+  WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   const bool need_xref = (a.mode != MODE_ITER);
   const bool need_init = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
@@ -152,11 +150,11 @@ __global__ void __launch_bounds__(32 * WPC * TEAM, 16 / (WPC * TEAM)) mpc_warp_s
       }
       mbar_wait(&bar_io, 0);
     } else {
-      for (int i = threadIdx.x; i < nvalid * nx; i += NTHR) {
+      for (int i = threadIdx.x; i < nvalid * nx; i += 32 * WPC) {
         sm.xref()[i] = a.xref[(size_t)base * nx + i];
         if (need_warm) sm.X()[i] = a.X[(size_t)base * nx + i];
       }
-      if (need_warm) for (int i = threadIdx.x; i < nvalid * nu; i += NTHR) sm.U()[i] = a.U[(size_t)base * nu + i];
+      if (need_warm) for (int i = threadIdx.x; i < nvalid * nu; i += 32 * WPC) sm.U()[i] = a.U[(size_t)base * nu + i];
       __syncthreads();
     }
   }
@@ -170,7 +168,7 @@ __global__ void __launch_bounds__(32 * WPC * TEAM, 16 / (WPC * TEAM)) mpc_warp_s
   } else {
     // resume: the slab image comes back by one TMA bulk copy per warp, the per-problem scalars by plain loads
     if (valid) {
-      if (lane == 0 && part == 0) {
+      if (lane == 0) {
         const uint32_t bytes = (uint32_t)((size_t)L.words * sizeof(T));
         mbar_expect_tx(&bar_w[wid], bytes);
         tma_load_1d(sm.slab(wid), a.slab + (size_t)b * L.words, bytes, &bar_w[wid]);
@@ -190,7 +188,7 @@ __global__ void __launch_bounds__(32 * WPC * TEAM, 16 / (WPC * TEAM)) mpc_warp_s
     // solution back to float64 row-major (rho is added back in float64), staging -> HBM
     if (valid && !skip) {
       S.store(sm.xref(wid), sm.X(wid), sm.U(wid));
-      if (lane == 0 && part == 0) {
+      if (lane == 0) {
         if (a.status) a.status[b] = st.status;
         if (a.iters) a.iters[b] = st.iters + (a.refine && a.iters ? a.iters[b] : 0);
       }
@@ -205,15 +203,15 @@ __global__ void __launch_bounds__(32 * WPC * TEAM, 16 / (WPC * TEAM)) mpc_warp_s
       }
     } else {
       __syncthreads();
-      for (int i = threadIdx.x; i < nvalid * nx; i += NTHR) a.X[(size_t)base * nx + i] = sm.X()[i];
-      for (int i = threadIdx.x; i < nvalid * nu; i += NTHR) a.U[(size_t)base * nu + i] = sm.U()[i];
+      for (int i = threadIdx.x; i < nvalid * nx; i += 32 * WPC) a.X[(size_t)base * nx + i] = sm.X()[i];
+      for (int i = threadIdx.x; i < nvalid * nu; i += 32 * WPC) a.U[(size_t)base * nu + i] = sm.U()[i];
     }
   } else if (valid) {
     // keep the slab + scalars for the next launch
-    w.team_sync();
+    __syncwarp();
     fence_async_smem();
-    w.team_sync();
-    if (lane == 0 && part == 0) {
+    __syncwarp();
+    if (lane == 0) {
       tma_store_1d(a.slab + (size_t)b * L.words, sm.slab(wid), (uint32_t)((size_t)L.words * sizeof(T)));
       tma_store_commit_wait();
       a.state[b] = st;
@@ -276,7 +274,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __
   double* my_U = sm.U(wid);
   const WarpCtx w;
   T obs[6];
-  WarpSolver<T, 1> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
+  WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   double x[5];
   for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
@@ -384,9 +382,7 @@ static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
 template <typename T, int WPC>
 static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s, size_t smem) {
   const int ctas = (a.B + WPC - 1) / WPC;
-  // small batches are latency-bound (one wave, idle issue slots): give every problem a 2-warp team
-  if (h->cfg.team_max_batch > 0 && a.B <= h->cfg.team_max_batch) mpc_warp_solve_kernel<T, WPC, 2><<<ctas, 64 * WPC, smem, s>>>(a);
-  else mpc_warp_solve_kernel<T, WPC, 1><<<ctas, 32 * WPC, smem, s>>>(a);
+  mpc_warp_solve_kernel<T, WPC><<<ctas, 32 * WPC, smem, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
@@ -414,9 +410,7 @@ static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t
 // opt the handle's kernel instantiations in to their dynamic shared memory size (once, at create)
 template <typename T, int WPC>
 static cudaError_t configure_kernels_t(size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }

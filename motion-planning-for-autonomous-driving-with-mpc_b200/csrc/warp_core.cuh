@@ -61,14 +61,12 @@ enum : int {
 enum : int { E03 = 0, E04, E13, E14, E42, E43 };
 enum : int { H00 = 0, H01, H04, H11, H14, H44, H22, H33 };
 
-enum : int { XCH_SLOTS = 8, XCH_WORDS = 2 * 2 * XCH_SLOTS };   // team exchange: [parity][part][slot]
 struct WLayout {
-  int N, o_state, o_rec, o_xch, words;
+  int N, o_state, o_rec, words;
   MPC_HD explicit WLayout(int N_) : N(N_) {
     o_state = 0;
     o_rec = ST_STRIDE * (N + 1);
-    o_xch = o_rec + REC_STRIDE * N;
-    words = (o_xch + XCH_WORDS + 3) & ~3;          // multiple of 4 words: 16-byte granularity for bulk copies
+    words = (o_rec + REC_STRIDE * N + 3) & ~3;     // multiple of 4 words: 16-byte granularity for bulk copies
   }
 };
 
@@ -150,12 +148,7 @@ struct SlabRef {
 };
 #endif
 
-// TEAM = 1: one warp does everything.  TEAM = 2: a 2-warp team per problem -- warp 0 ("A") runs the two serial sweeps and,
-// in the stage-parallel phases, the dynamics + control rows; warp 1 ("B") the state rows, the obstacle rows and the x-cost.
-// The warps meet at named barriers (WarpCtx::team_sync) and exchange their partial reductions through the slab's XCH
-// area, combined in a fixed order so both warps hold bit-identical uniform values.  Used for batches small enough to
-// be latency-bound (the helper warp's issue slots are idle otherwise); TEAM = 1 is the throughput configuration.
-template <typename T, int TEAM = 1>
+template <typename T>
 struct WarpSolver {
   const ParamsT<T>& P;
   const WLayout L;
@@ -163,31 +156,11 @@ struct WarpSolver {
   const T* obs;      // obstacle circle centres (centre, front, rear) in the problem's shifted frame
   const WarpCtx& w;
   const int lane;
-  const int part;    // 0 = warp A, 1 = warp B (always 0 for TEAM = 1)
-  const bool doA, doB;
-  mutable int xpar;  // parity of the next team exchange
   const LaneTab tb;
   const T il_wb;     // 1 / wheelbase
 
-  MPC_HD WarpSolver(const ParamsT<T>& P_, const SlabRef<T>& slab, const T* obs_, const WarpCtx& w_, int part_ = 0)
-      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), part(TEAM == 1 ? 0 : part_),
-        doA(TEAM == 1 || part_ == 0), doB(TEAM == 1 || part_ == 1), xpar(0), tb(w_.lane()), il_wb(T(1) / P_.l_wb) {}
-
-  // end of a phase: make this phase's shared-memory writes visible to the consumer lanes (and to the other warp)
-  MPC_HD void phase_sync() const { if (TEAM == 1) w.sync(); else w.team_sync(); }
-  // team exchange of n <= XCH_SLOTS warp-uniform partial values: mine[] in, other[] = the other warp's values out
-  MPC_HD void team_exchange(const T* mine, T* other, int n) const {
-    T* xs = &sl[L.o_xch + (xpar * 2) * XCH_SLOTS];
-    if (lane == 0) for (int i = 0; i < n; ++i) xs[part * XCH_SLOTS + i] = mine[i];
-    w.team_sync();
-    for (int i = 0; i < n; ++i) other[i] = xs[(1 - part) * XCH_SLOTS + i];
-    xpar ^= 1;
-  }
-  MPC_HD T team_sum(T v) const {       // fixed order: A's value + B's value
-    if (TEAM == 1) return v;
-    T o; team_exchange(&v, &o, 1);
-    return part == 0 ? v + o : o + v;
-  }
+  MPC_HD WarpSolver(const ParamsT<T>& P_, const SlabRef<T>& slab, const T* obs_, const WarpCtx& w_)
+      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()), il_wb(T(1) / P_.l_wb) {}
 
   MPC_HD T& sx(int k, int f) const { return sl[L.o_state + ST_STRIDE * k + f]; }
   MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + REC_STRIDE * k + f]; }
@@ -246,7 +219,6 @@ struct WarpSolver {
     const int N = P.N;
     const double ox = xref[0], oy = xref[1];
     for (int j = 0; j < 3; ++j) { obs_out[2 * j] = (T)(obstacle_abs[2 * j] - ox); obs_out[2 * j + 1] = (T)(obstacle_abs[2 * j + 1] - oy); }
-    if (doA)
     for (int k = lane; k <= N; k += 32) {
       const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
       const double* xin = (k == 0 || !Xin) ? xref : (Xin + 5 * k);   // stage 0 is pinned to X_ref[:,0]; no warm start = X_0 tiled
@@ -260,8 +232,8 @@ struct WarpSolver {
         rc(k, R_ZERO) = T(0); rc(k, R_ONE) = T(1);
       }
     }
-    if (doA) w.sync();
-    if (P.init_rollout && doA) {
+    w.sync();
+    if (P.init_rollout) {
       // single-shooting start: x_{k+1} = x_k + dt f(x_k, u_k) from the pinned state (float64, every lane redundantly;
       // lane k % 32 keeps stage k+1).  The caller's X rows are ignored.
       double x[5];
@@ -278,18 +250,16 @@ struct WarpSolver {
       }
       w.sync();
     }
-    phase_sync();
   }
   MPC_HD void store(const double* xref, double* Xout, double* Uout) const {
     const int N = P.N;
-    phase_sync();
-    if (doA)
+    w.sync();
     for (int k = lane; k <= N; k += 32) {
       const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
       for (int j = 0; j < 5; ++j) Xout[5 * k + j] = (k == 0) ? xref[j] : ((double)sx(k, S_XT + j) + rho[j]);
       if (k < N) { Uout[2 * k] = (double)rc(k, R_U); Uout[2 * k + 1] = (double)rc(k, R_U + 1); }
     }
-    phase_sync();
+    w.sync();
   }
 
   // ---------------------------------------------------------------- initialisation (lane = stage)
@@ -317,13 +287,12 @@ struct WarpSolver {
     }
     if (bad) { st.status = ST_INFEASIBLE_X0; st.done = 1; }
     const T kp = P.bound_push;
-    if (lane == 0 && doA) {
+    if (lane == 0) {
       const Trig t = trig_of(xa(0, 4), xa(0, 2));
       sx(0, S_TR) = t.sn; sx(0, S_TR + 1) = t.cs; sx(0, S_TR + 2) = t.tn;
       sx(0, S_TRT) = t.sn; sx(0, S_TRT + 1) = t.cs; sx(0, S_TRT + 2) = t.tn;
       for (int j = 0; j < 5; ++j) sx(0, S_XTT + j) = sx(0, S_XT + j);
     }
-    if (doA)
     for (int k = lane; k < N; k += 32) {
       const T mu = st.mu;
       const T pdd = m_min(kp, kp * (P.dd_max - P.dd_min));
@@ -363,7 +332,7 @@ struct WarpSolver {
       for (int j = 0; j < 5; ++j) rc(k, R_DX + j) = T(0);
       rc(k, R_DU) = T(0); rc(k, R_DU + 1) = T(0);
     }
-    phase_sync();
+    w.sync();
   }
 
   // ---------------------------------------------------------------- phase A: stage KKT blocks (lane = stage)
@@ -380,7 +349,6 @@ struct WarpSolver {
       t0.sn = sx(k, S_TR); t0.cs = sx(k, S_TR + 1); t0.tn = sx(k, S_TR + 2);
       t1.sn = sx(k + 1, S_TR); t1.cs = sx(k + 1, S_TR + 1);
       const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
-      if (doA) {
       // dynamics: A_k = I + dt*df/dx (configuration.py:364-368), defect
       const T sec2 = T(1) + t0.tn * t0.tn;
       rc(k, R_E + E03) = dt * t0.cs; rc(k, R_E + E04) = -dt * v * t0.sn;
@@ -390,8 +358,6 @@ struct WarpSolver {
       defect(k, x0d, x1d, v, t0, u0, u1, d);
 #pragma unroll
       for (int j = 0; j < 5; ++j) rc(k, R_D + j) = d[j];
-      }
-      if (doB) {
       // x_{k+1} terms: cost (stages 1..N-1 only, quirk Q1), box barriers, obstacle barriers
       T hd[5], g[5], lc[5];
 #pragma unroll
@@ -438,9 +404,8 @@ struct WarpSolver {
       rc(k, R_H + H14) = h14; rc(k, R_H + H44) = hd[4]; rc(k, R_H + H22) = hd[2]; rc(k, R_H + H33) = hd[3];
 #pragma unroll
       for (int j = 0; j < 5; ++j) { rc(k, R_GX + j) = g[j]; rc(k, R_LC + j) = lc[j]; }
-      }
       // control terms
-      if (doA) {
+      {
         const T ilo = m_rcp(m_slack(u0 - P.dd_min)), ihi = m_rcp(m_slack(P.dd_max - u0));
         T Ru0 = T(2) * P.R[0] + rc(k, R_V + V_DD_LO) * ilo + rc(k, R_V + V_DD_HI) * ihi;
         T ru0 = T(2) * P.R[0] * u0 + mu * (ihi - ilo);
@@ -456,7 +421,7 @@ struct WarpSolver {
         rc(k, R_RU) = Ru0; rc(k, R_RU + 1) = Ru1; rc(k, R_RU + 2) = ru0 * idt; rc(k, R_RU + 3) = ru1 * idt;
       }
     }
-    phase_sync();
+    w.sync();
   }
 
   // ---------------------------------------------------------------- phase C: backward Riccati sweep (lane = entry of [P | p])
@@ -622,23 +587,19 @@ struct WarpSolver {
       const T v = x0d[3] + sx(k, S_XR + 3);
       const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
       const T du0 = rc(k, R_DU), du1 = rc(k, R_DU + 1);
-      if (doA) {
 #pragma unroll
       for (int j = 0; j < 5; ++j) { o.c1 += m_abs(d[j]); o.mag += m_abs(x0d[j]) + m_abs(x1d[j]); }
       o.mag += dt * (T(2) * m_abs(v) + m_abs(u0) + m_abs(u1)) + m_abs(rc(k, R_CP)) + m_abs(rc(k, R_CP + 1));
       o.dphi += T(2) * P.R[0] * u0 * du0 + T(2) * P.R[1] * u1 * du1;
+      if (k + 1 <= N - 1) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) o.dphi += T(2) * P.Q[j] * x1d[j] * nx[j];
+      }
       row_limits(m_slack(u0 - P.dd_min), rc(k, R_V + V_DD_LO), du0, mu, tau, o);
       row_limits(m_slack(P.dd_max - u0), rc(k, R_V + V_DD_HI), -du0, mu, tau, o);
       const T ahi = (k == 0) ? st.a0_hi : P.a_max;
       row_limits(m_slack(ahi - u1), rc(k, R_V + V_A_HI), -du1, mu, tau, o);
       if (k == 0) row_limits(m_slack(u1 - st.a0_lo), rc(k, R_V + V_A_LO), du1, mu, tau, o);
-      o.step_inf = m_max(o.step_inf, m_max(m_abs(du0), m_abs(du1)));
-      }
-      if (doB) {
-      if (k + 1 <= N - 1) {
-#pragma unroll
-        for (int j = 0; j < 5; ++j) o.dphi += T(2) * P.Q[j] * x1d[j] * nx[j];
-      }
       row_limits(m_slack(x1a[2] - P.de_min), rc(k, R_V + V_DE_LO), nx[2], mu, tau, o);
       row_limits(m_slack(P.de_max - x1a[2]), rc(k, R_V + V_DE_HI), -nx[2], mu, tau, o);
       row_limits(m_slack(x1a[3] - P.v_min), rc(k, R_V + V_V_LO), nx[3], mu, tau, o);
@@ -657,31 +618,20 @@ struct WarpSolver {
       }
 #pragma unroll
       for (int j = 0; j < 5; ++j) o.step_inf = m_max(o.step_inf, m_abs(nx[j]));
-      }
+      o.step_inf = m_max(o.step_inf, m_max(m_abs(du0), m_abs(du1)));
     }
     const bool fin = m_finite(o.step_inf) && m_finite(o.dphi) && m_finite(o.a_p) && m_finite(o.a_d);
-    bool allfin = w.all(fin);
+    const bool allfin = w.all(fin);
 #ifdef MPC_DIAG
     { const T mine = o.a_p; const T mx = w.max_nonneg(m_max(o.a_p, T(0))); int code = (mine == mx) ? o.blk : -1;
       for (int m = 16; m; m >>= 1) { const int other = w.shfl_xor(code, m); code = code > other ? code : other; }
       o.blk = code; }
 #endif
     o.a_p = w.max_nonneg(m_max(o.a_p, T(0))); o.a_d = w.max_nonneg(m_max(o.a_d, T(0)));
-    o.step_inf = w.max_nonneg(fin ? o.step_inf : T(0));
-    o.dphi = w.sum(o.dphi); o.c1 = w.sum(o.c1); o.mag = w.sum(o.mag);
-    if (TEAM == 2) {
-      // combine the two warps' partial results (fixed order A op B, identical in both warps)
-      const T mine[7] = {o.a_p, o.a_d, o.step_inf, o.dphi, o.c1, o.mag, allfin ? T(1) : T(0)};
-      T oth[7];
-      team_exchange(mine, oth, 7);
-      const T* A = part == 0 ? mine : oth;
-      const T* B = part == 0 ? oth : mine;
-      o.a_p = m_max(A[0], B[0]); o.a_d = m_max(A[1], B[1]); o.step_inf = m_max(A[2], B[2]);
-      o.dphi = A[3] + B[3]; o.c1 = A[4] + B[4]; o.mag = A[5] + B[5];
-      allfin = (A[6] != T(0)) && (B[6] != T(0));
-    }
     o.a_p = (o.a_p > tau) ? tau / o.a_p : T(1);
     o.a_d = (o.a_d > tau) ? tau / o.a_d : T(1);
+    o.step_inf = w.max_nonneg(fin ? o.step_inf : T(0));
+    o.dphi = w.sum(o.dphi); o.c1 = w.sum(o.c1); o.mag = w.sum(o.mag);
     if (!allfin) o.step_inf = T(NAN);     // the caller turns this into ST_NAN
     return o;
   }
@@ -691,19 +641,13 @@ struct WarpSolver {
   MPC_HD void trial_points(T al) const {
     const int N = P.N;
     for (int k = lane; k < N; k += 32) {
-      if (doA) {                                   // trial state + sin/cos of its heading
-        T xb[5];
+      T xb[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) { xb[j] = sx(k + 1, S_XT + j) + al * rc(k, R_DX + j); sx(k + 1, S_XTT + j) = xb[j]; }
-        T sn, cs; m_sincos(xb[4] + sx(k + 1, S_XR + 4), &sn, &cs);
-        sx(k + 1, S_TRT) = sn; sx(k + 1, S_TRT + 1) = cs;
-      }
-      if (doB) {                                   // tan of its steering angle
-        const T de = (sx(k + 1, S_XT + 2) + al * rc(k, R_DX + 2)) + sx(k + 1, S_XR + 2);
-        sx(k + 1, S_TRT + 2) = m_tan(de);
-      }
+      for (int j = 0; j < 5; ++j) { xb[j] = sx(k + 1, S_XT + j) + al * rc(k, R_DX + j); sx(k + 1, S_XTT + j) = xb[j]; }
+      const Trig t = trig_of(xb[4] + sx(k + 1, S_XR + 4), xb[2] + sx(k + 1, S_XR + 2));
+      sx(k + 1, S_TRT) = t.sn; sx(k + 1, S_TRT + 1) = t.cs; sx(k + 1, S_TRT + 2) = t.tn;
     }
-    phase_sync();
+    w.sync();
   }
   // second-order correction: re-simulate the trial states from the trial controls,
   //   x^_{k+1} = x^_k + dt f(x^_k, u_k + al*du_k) - (1 - al) d_k,
@@ -711,7 +655,6 @@ struct WarpSolver {
   // the multiplier / slack updates of commit() see it.  Serial in k, computed redundantly by every lane (rare path).
   MPC_HD void trial_points_reshoot(T al) const {
     const int N = P.N;
-    if (!doA) { phase_sync(); return; }
     T xd[5], xaa[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) { xd[j] = sx(0, S_XT + j); xaa[j] = xd[j] + sx(0, S_XR + j); }
@@ -736,7 +679,7 @@ struct WarpSolver {
         sx(k + 1, S_TRT) = ta.sn; sx(k + 1, S_TRT + 1) = ta.cs; sx(k + 1, S_TRT + 2) = ta.tn;
       }
     }
-    phase_sync();
+    w.sync();
   }
 
   // dphi: cost + barrier difference (term by term, no cancellation); c1: l1 infeasibility at the trial point;
@@ -757,6 +700,8 @@ struct WarpSolver {
 #pragma unroll
       for (int i = 0; i < 12; ++i) rts[i] = T(0);
       if (act) {
+      int nr = 0;
+      auto lrow = [&](T num, T den) { rts[nr++] = num * m_rcp(den); };
       const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
       const T du0 = al * rc(k, R_DU), du1 = al * rc(k, R_DU + 1);
       const T nu0 = u0 + du0, nu1 = u1 + du1;
@@ -770,7 +715,6 @@ struct WarpSolver {
         x1d[j] = sx(k + 1, S_XT + j);
         x1a[j] = x1d[j] + sx(k + 1, S_XR + j);
       }
-      if (doA) {
       Trig ta; ta.sn = sx(k, S_TRT); ta.cs = sx(k, S_TRT + 1); ta.tn = sx(k, S_TRT + 2);
       T d[5];
       if (reshoot) {
@@ -792,17 +736,14 @@ struct WarpSolver {
           dphi += t0; nz += m_abs(t0);
         }
       }
-      rts[0] = du0 * m_rcp(m_slack(u0 - P.dd_min));
-      rts[1] = -du0 * m_rcp(m_slack(P.dd_max - u0));
+      lrow(du0, m_slack(u0 - P.dd_min));
+      lrow(-du0, m_slack(P.dd_max - u0));
       const T ahi = (k == 0) ? st.a0_hi : P.a_max;
-      rts[2] = -du1 * m_rcp(m_slack(ahi - u1));
-      if (k == 0) rts[10] = du1 * m_rcp(m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side
-      }
-      if (doB) {
-      rts[3] = dxb[2] * m_rcp(m_slack(x1a[2] - P.de_min));
-      rts[4] = -dxb[2] * m_rcp(m_slack(P.de_max - x1a[2]));
-      rts[5] = dxb[3] * m_rcp(m_slack(x1a[3] - P.v_min));
-      rts[6] = -dxb[3] * m_rcp(m_slack(P.v_max - x1a[3]));
+      lrow(-du1, m_slack(ahi - u1));
+      lrow(dxb[2], m_slack(x1a[2] - P.de_min));
+      lrow(-dxb[2], m_slack(P.de_max - x1a[2]));
+      lrow(dxb[3], m_slack(x1a[3] - P.v_min));
+      lrow(-dxb[3], m_slack(P.v_max - x1a[3]));
       // obstacle rows: the slack moves with its own Newton step ds (from the OLD linearisation)
       const T sn0 = sx(k + 1, S_TR), cs0 = sx(k + 1, S_TR + 1);
       const T snb = sx(k + 1, S_TRT), csb = sx(k + 1, S_TRT + 1);
@@ -818,7 +759,7 @@ struct WarpSolver {
         c1 += m_resid((hb - P.r_sum) - (s + ds), hb);
       }
       }
-      }
+      if (k == 0) rts[10] = du1 * m_rcp(m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side
       }   // act
       bool small = true;
 #pragma unroll
@@ -842,15 +783,6 @@ struct WarpSolver {
     nz += mu * lga;
     ok = w.all(ok);
     dphi = w.sum(dphi); c1 = w.sum(c1); nz = w.sum(nz);
-    if (TEAM == 2) {
-      const T mine[4] = {dphi, c1, nz, ok ? T(1) : T(0)};
-      T oth[4];
-      team_exchange(mine, oth, 4);
-      const T* A = part == 0 ? mine : oth;
-      const T* B = part == 0 ? oth : mine;
-      dphi = A[0] + B[0]; c1 = A[1] + B[1]; nz = A[2] + B[2];
-      ok = (A[3] != T(0)) && (B[3] != T(0));
-    }
     return ok;
   }
 
@@ -881,15 +813,11 @@ struct WarpSolver {
         rc(k, R_V + slot) = nn;
         const T c = snew * nn; sum += c; cmax = m_max(cmax, c);
       };
-      if (doA) {
       upd(V_DD_LO, m_slack(u0 - P.dd_min), du0, m_slack(nu0 - P.dd_min));
       upd(V_DD_HI, m_slack(P.dd_max - u0), -du0, m_slack(P.dd_max - nu0));
       const T ahi = (k == 0) ? st.a0_hi : P.a_max;
       upd(V_A_HI, m_slack(ahi - u1), -du1, m_slack(ahi - nu1));
       if (k == 0) upd(V_A_LO, m_slack(u1 - st.a0_lo), du1, m_slack(nu1 - st.a0_lo));
-      rc(k, R_U) = nu0; rc(k, R_U + 1) = nu1;
-      }
-      if (doB) {
       upd(V_DE_LO, m_slack(x1a[2] - P.de_min), dx[2], m_slack(nde - P.de_min));
       upd(V_DE_HI, m_slack(P.de_max - x1a[2]), -dx[2], m_slack(P.de_max - nde));
       upd(V_V_LO, m_slack(x1a[3] - P.v_min), dx[3], m_slack(nvv - P.v_min));
@@ -909,34 +837,23 @@ struct WarpSolver {
       } else {
         sum += T(3) * mu;                          // screened rows sit on the central path: s*nu = mu
       }
+      rc(k, R_U) = nu0; rc(k, R_U + 1) = nu1;
 #pragma unroll
       for (int j = 0; j < 5; ++j) sx(k + 1, S_XT + j) = xn[j];
       sx(k + 1, S_TR) = sx(k + 1, S_TRT); sx(k + 1, S_TR + 1) = sx(k + 1, S_TRT + 1); sx(k + 1, S_TR + 2) = sx(k + 1, S_TRT + 2);
-      }
     }
     sum = w.sum(sum);
     cmax = w.max_nonneg(m_max(cmax, T(0)));
-    if (TEAM == 2) {
-      const T mine[2] = {sum, cmax};
-      T oth[2];
-      team_exchange(mine, oth, 2);          // its barrier also publishes this phase's U / X / multiplier updates
-      sum = part == 0 ? mine[0] + oth[0] : oth[0] + mine[0];
-      cmax = m_max(mine[1], oth[1]);
-    } else {
-      w.sync();
-    }
     avg = sum / T(10 * N + 1);
+    w.sync();
   }
 
   // ---------------------------------------------------------------- one SQP / interior-point iteration (uniform control flow)
   MPC_HD void iterate(ProbState<T>& st) const {
     if (st.done) return;
     linearize(st);
-    if (doA) {                                     // the two serial sweeps: one warp; its team mate waits at the barrier
-      if (!backward(P.hessian)) backward(HESS_GN);
-      forward_sweep();
-    }
-    if (TEAM == 2) w.team_sync();
+    if (!backward(P.hessian)) backward(HESS_GN);
+    forward_sweep();
     FwdOut f = forward_stats(st);
     if (!m_finite(f.step_inf) || !m_finite(f.dphi)) { st.status = ST_NAN; st.done = 1; return; }
     // penalty parameter of the l1 merit (left alone once the infeasibility is at its rounding-noise floor: dividing by
@@ -973,8 +890,7 @@ struct WarpSolver {
         noise = T(8) * epsm * (nz + st.rho * f.mag);
         if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; st.nsoc++; break; }
         // the re-simulated step replaced DX: restore the Newton step for the shorter trials
-        if (doA) forward_sweep();
-        if (TEAM == 2) w.team_sync();
+        forward_sweep();
       }
       al *= T(0.5);
     }
@@ -1010,12 +926,11 @@ struct WarpSolver {
       if (al >= T(0.5)) st.centered = 1;
       else if (al < P.mu_up_alpha && st.mu * P.mu_up_factor <= P.mu_max) {
         st.mu *= P.mu_up_factor;
-        if (doA)
         for (int k = lane; k < P.N; k += 32) {
 #pragma unroll
           for (int j = 0; j < NV; ++j) rc(k, R_V + j) *= P.mu_up_factor;
         }
-        phase_sync();
+        w.sync();
         return;
       }
     }

@@ -32,16 +32,8 @@ namespace mpcb200 {
 #endif
 struct WarpCtx {
   static constexpr unsigned FULL = 0xffffffffu;
-  int team_bar;      // named barrier of this problem's 2-warp team (0: the problem has one warp)
-  MPC_HD explicit WarpCtx(int team_bar_ = 0) : team_bar(team_bar_) {}
   MPC_HD int lane() const { return MPC_WARP_DEV((int)(threadIdx.x & 31u), 0); }
   MPC_HD void sync() const { MPC_WARP_DEV(__syncwarp(), (void)0); }
-  // barrier over the 64 threads of a 2-warp team (also orders their shared-memory accesses)
-  MPC_HD void team_sync() const {
-#if defined(__CUDA_ARCH__)
-    if (team_bar) asm volatile("bar.sync %0, 64;" ::"r"(team_bar) : "memory"); else __syncwarp();
-#endif
-  }
   MPC_HD float shfl(float v, int src) const { return MPC_WARP_DEV(__shfl_sync(FULL, v, src), v); }
   MPC_HD double shfl(double v, int src) const { return MPC_WARP_DEV(__shfl_sync(FULL, v, src), v); }
   MPC_HD int shfl(int v, int src) const { return MPC_WARP_DEV(__shfl_sync(FULL, v, src), v); }
@@ -86,14 +78,13 @@ struct WarpCtx {
 namespace mpcb200 {
 
 struct HostWarp {
-  static constexpr int NL = 64;             // up to two warps (a 2-warp team per problem)
+  static constexpr int NL = 32;
   static constexpr size_t STACK = 512 * 1024;
   ucontext_t main_ctx, lane_ctx[NL];
   std::vector<char> stacks;
-  uint64_t xbuf[2][2][32];                  // [warp][parity][lane]
+  uint64_t xbuf[2][NL];
   bool finished[NL];
-  int cur, nl;
-  long team_count;                          // arrivals at team barriers since run()
+  int cur;
   void (*body)(int lane, void* arg);
   void* arg;
   HostWarp() : stacks(STACK * NL) {}
@@ -107,8 +98,8 @@ struct HostWarp {
   }
   // hand control to the next unfinished lane (round-robin); to main when all are finished
   void yield_from(int lane) {
-    for (int s = 1; s <= nl; ++s) {
-      const int nxt = (lane + s) % nl;
+    for (int s = 1; s <= NL; ++s) {
+      const int nxt = (lane + s) % NL;
       if (!finished[nxt]) {
         if (nxt == lane) return;
         cur = nxt;
@@ -118,9 +109,9 @@ struct HostWarp {
     }
     swapcontext(&lane_ctx[lane], &main_ctx);
   }
-  void run(void (*f)(int, void*), void* a, int nlanes = 32) {
-    body = f; arg = a; active() = this; nl = nlanes; team_count = 0;
-    for (int l = 0; l < nl; ++l) {
+  void run(void (*f)(int, void*), void* a) {
+    body = f; arg = a; active() = this;
+    for (int l = 0; l < NL; ++l) {
       finished[l] = false;
       getcontext(&lane_ctx[l]);
       lane_ctx[l].uc_stack.ss_sp = stacks.data() + STACK * l;
@@ -136,26 +127,18 @@ struct HostWarp {
 
 struct WarpCtx {
   HostWarp* hw;
-  int gl_;           // fiber index (0..63)
-  int lane_, warp_;
+  int lane_;
   mutable int par;
-  mutable long team_gen;
-  WarpCtx(HostWarp* h, int l) : hw(h), gl_(l), lane_(l & 31), warp_(l >> 5), par(0), team_gen(0) {}
+  WarpCtx(HostWarp* h, int l) : hw(h), lane_(l), par(0) {}
   int lane() const { return lane_; }
-  void sync() const { hw->yield_from(gl_); }
-  // barrier over all fibers of the run (the 2-warp team); a lone warp degenerates to sync()
-  void team_sync() const {
-    ++team_gen;
-    ++hw->team_count;
-    do { hw->yield_from(gl_); } while (hw->team_count < team_gen * hw->nl);
-  }
+  void sync() const { hw->yield_from(lane_); }
   template <typename T> T xchg(T v, int src) const {
     uint64_t bits = 0;
     memcpy(&bits, &v, sizeof(T));
-    hw->xbuf[warp_][par][lane_] = bits;
-    hw->yield_from(gl_);
+    hw->xbuf[par][lane_] = bits;
+    hw->yield_from(lane_);
     T out;
-    const uint64_t b = hw->xbuf[warp_][par][src & 31];
+    const uint64_t b = hw->xbuf[par][src & 31];
     memcpy(&out, &b, sizeof(T));
     par ^= 1;
     return out;

@@ -22,12 +22,12 @@ struct Job {
   double kkt;
 };
 
-template <typename T, int TEAM>
+template <typename T>
 static void lane_body(int lane, void* arg) {
   Job<T>& J = *(Job<T>*)arg;
   WarpCtx w(J.hw, lane);
   T obs[6];
-  WarpSolver<T, TEAM> S(J.P, SlabRef<T>{J.slab, 0}, obs, w, lane >> 5);
+  WarpSolver<T> S(J.P, SlabRef<T>{J.slab, 0}, obs, w);
   S.load(J.xref, J.X, J.U, J.cfg->obstacle, obs);
   ProbState<T> st;
   S.init(st);
@@ -43,7 +43,7 @@ static void lane_body(int lane, void* arg) {
 
 template <typename T>
 static void run(const mpcb200_config& cfg, const double* xref, double* Xio, double* Uio, int* status, int* iters,
-                double* kkt, int B, int trace, int team) {
+                double* kkt, int B, int trace) {
   const int N = cfg.N;
   WLayout L(N);
   std::vector<T> buf(L.words + REC_STRIDE + 4);   // + one record: the forward sweep prefetches one record past the end
@@ -54,7 +54,7 @@ static void run(const mpcb200_config& cfg, const double* xref, double* Xio, doub
     J.xref = xref + (size_t)b * 5 * (N + 1); J.X = Xio + (size_t)b * 5 * (N + 1); J.U = Uio + (size_t)b * 2 * N;
     J.hw = &hw; J.trace = trace; J.status = 0; J.iters = 0; J.kkt = 0; J.nsoc = 0;
     for (auto& v : buf) v = T(NAN);        // catch reads of never-written slab words
-    if (team == 2) hw.run(&lane_body<T, 2>, &J, 64); else hw.run(&lane_body<T, 1>, &J, 32);
+    hw.run(&lane_body<T>, &J);
     if (status) status[b] = J.status;
     if (iters) iters[b] = J.iters;
     if (kkt) kkt[b] = trace == 3 ? (double)J.nsoc : J.kkt;
@@ -63,15 +63,10 @@ static void run(const mpcb200_config& cfg, const double* xref, double* Xio, doub
 
 extern "C" {
 void hostsim_default_config(mpcb200_config* c, int N, int precision) { default_config(c, N, precision); }
-// team = 1: one warp per problem; team = 2: the 2-warp team mapping (64 fibers)
-int hostsim_solve_team(const mpcb200_config* cfg, const double* xref, double* X, double* U, int* status, int* iters,
-                       double* kkt, int B, int trace, int team) {
-  if (cfg->precision == MPCB200_F64) run<double>(*cfg, xref, X, U, status, iters, kkt, B, trace, team);
-  else run<float>(*cfg, xref, X, U, status, iters, kkt, B, trace, team);
-  return 0;
-}
 int hostsim_solve(const mpcb200_config* cfg, const double* xref, double* X, double* U, int* status, int* iters,
                   double* kkt, int B, int trace) {
-  return hostsim_solve_team(cfg, xref, X, U, status, iters, kkt, B, trace, 1);
+  if (cfg->precision == MPCB200_F64) run<double>(*cfg, xref, X, U, status, iters, kkt, B, trace);
+  else run<float>(*cfg, xref, X, U, status, iters, kkt, B, trace);
+  return 0;
 }
 }

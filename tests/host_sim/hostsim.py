@@ -19,8 +19,7 @@ class Config(C.Structure):
                  ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_factor", C.c_double), ("tol_step", C.c_double),
                  ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double), ("mu_min_alpha", C.c_double), ("mu_up_alpha", C.c_double), ("mu_up_factor", C.c_double), ("mu_max", C.c_double),
                  ("kappa_sigma", C.c_double), ("screen_inv_curv", C.c_double), ("trust_step", C.c_double), ("acc_factor", C.c_double),
-                 ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("team_max_batch", C.c_int32), ("reserved0", C.c_int32),
-                 ("init_rollout", C.c_int32)])
+                 ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32)])
 
 
 _lib = None
@@ -45,7 +44,7 @@ def default_config(N, precision=0):
     return c
 
 
-def solve(cfg, xref, X, U, trace=0, team=1):
+def solve(cfg, xref, X, U, trace=0):
     xref = np.ascontiguousarray(xref, np.float64)
     X = np.ascontiguousarray(X, np.float64).copy()
     U = np.ascontiguousarray(U, np.float64).copy()
@@ -54,5 +53,5 @@ def solve(cfg, xref, X, U, trace=0, team=1):
     it = np.zeros(B, np.int32)
     kkt = np.zeros(B, np.float64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    lib().hostsim_solve_team(C.byref(cfg), p(xref), p(X), p(U), p(st), p(it), p(kkt), B, trace, team)
+    lib().hostsim_solve(C.byref(cfg), p(xref), p(X), p(U), p(st), p(it), p(kkt), B, trace)
     return X, U, st, it, kkt

@@ -154,17 +154,3 @@ def test_shard_ranges_cover_batch():
             r = [shard_range(B, k, W) for k in range(W)]
             assert r[0][0] == 0 and r[-1][1] == B and all(r[k][1] == r[k + 1][0] for k in range(W - 1))
             assert sum(shard_sizes(B, W)) == B and max(shard_sizes(B, W)) - min(shard_sizes(B, W)) <= 1
-
-
-def test_two_warp_team_mapping_equals_single_warp_mapping():
-    """TEAM = 2 (warp A: sweeps + dynamics/control rows, warp B: state/obstacle rows; named barriers + exchange of the
-    partial reductions) is the same algorithm as TEAM = 1: same iteration counts, results equal to rounding."""
-    for name, N, seed, prec, tol in (("ZAM_Over-1_1_LF", 30, 20261017, 0, 2e-6), ("USA_Lanker-2_18_T-1_LF", 50, 20261019, 1, 1e-12),
-                                     ("ZAM_Over-1_1_CA", 30, 20261018, 1, 1e-4)):
-        sc, x0, xref, X, U = mpc_b200.make_batch(name, 4, N, seed)
-        cfg = _cfg(sc, N, prec, max_iter=200)
-        X1, U1, st1, it1, _ = hostsim.solve(cfg, xref, X, U, team=1)
-        X2, U2, st2, it2, _ = hostsim.solve(cfg, xref, X, U, team=2)
-        assert (st1 == 1).all() and (st2 == 1).all()
-        assert np.array_equal(it1, it2) or name.endswith("CA")
-        assert np.abs(U1 - U2).max() < tol and np.abs(X1 - X2).max() < tol
