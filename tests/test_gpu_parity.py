@@ -286,3 +286,27 @@ def test_float64_refinement_pass_converges_the_stalled_collision_avoidance_insta
         w = nlp.pack(Ur[b], Xr[b])
         r = ipm.solve(d, w)
         assert r["status"] == 1 and np.abs(r["w"] - w).max() < 1e-4          # was ~3e-3 before the refinement
+
+
+def test_long_horizon_and_small_horizon_edges():
+    """N = iter_length = 70 on USA_Lanker (frozen window, 3 stages per lane) and the smallest horizon N = 4."""
+    import mpc_b200
+    from oracle import nlp, ipm
+    for name, N, B in (("USA_Lanker-2_18_T-1_LF", 70, 33), ("ZAM_Over-1_1_LF", 4, 5)):
+        sc, opt = _opt(name, N, "f32", max_batch=64, max_iter=200)
+        _, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 77)
+        U, X, st, it = _np(*opt.solve_batch(xref))
+        assert (st == 1).all(), (name, st, it)
+        for b in (0, B - 1):
+            d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+            r = ipm.solve(d, nlp.pack(U0[b], X0[b]))
+            if r["status"] != 1:
+                continue
+            Uo, Xo = nlp.split(r["w"], N)
+            assert np.abs(U[b] - Uo).max() < 1e-3 and np.abs(X[b] - Xo).max() < 1e-3
+    with pytest.raises(Exception):
+        _opt("ZAM_Over-1_1_LF", 3, "f32", max_batch=8)            # N < 4 is rejected at create
+    sc, opt = _opt("ZAM_Over-1_1_LF", 30, "f32", max_batch=8)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", 16, 30, 1)
+    with pytest.raises(Exception):
+        opt.solve_batch(xref)                                     # B > max_batch is an API error, not a crash
