@@ -120,9 +120,13 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
                         double desired_velocity, const double* d_x0, double* d_traj, double* d_ctrl,
                         int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
-/* Host-buffer entry point (the end-to-end path): H2D of xref / X / U warm start, solve, D2H of the optimal X / U /
- * status / iters, pipelined in chunks over internal streams; synchronous on return.  h_X_out / h_U_out may alias
- * h_X / h_U (in place).  h_X = h_U = NULL: cold start (X_0 tiled, zero controls), only xref is uploaded.  Host buffers should be pinned (pageable ones work but serialise the pipeline). */
+/* Host-buffer entry point (the end-to-end path); synchronous on return.  h_X_out / h_U_out may alias h_X / h_U (in
+ * place).  h_X = h_U = NULL: cold start (X_0 tiled, zero controls), only xref is read.
+ *   - every data buffer pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()): ZERO-COPY route -- one launch
+ *     whose TMA bulk copies read xref (+ warm start) from and write X / U to host memory directly over PCIe, so each
+ *     problem's transfer overlaps the other problems' iterations and no staging copy sits on the critical path;
+ *   - otherwise (pageable buffers, or MPCB200_HOST_STAGED=1): H2D, solve and D2H through library-owned device staging,
+ *     pipelined in chunks over internal streams.  Same arithmetic, bit-identical results either way. */
 int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U,
                        double* h_X_out, double* h_U_out, int32_t* h_status, int32_t* h_iters, int32_t B);
 

@@ -310,3 +310,39 @@ def test_long_horizon_and_small_horizon_edges():
     _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", 16, 30, 1)
     with pytest.raises(Exception):
         opt.solve_batch(xref)                                     # B > max_batch is an API error, not a crash
+
+
+def test_host_path_zero_copy_route_is_bit_identical_to_the_staged_route_and_the_device_path(monkeypatch):
+    """mpcb200_solve_host with pinned buffers = ONE launch whose TMA bulk copies read / write host memory directly;
+    with pageable buffers (or MPCB200_HOST_STAGED=1) = staged copy pipeline.  Same arithmetic either way."""
+    import torch
+    import mpc_b200
+    N, B = 30, 257                                                    # odd: the last CTA tile is ragged (plain-loop I/O)
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=512)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 77)
+    Ua, Xa, sta, ita = _np(*opt.solve_batch(xref))
+    pin = lambda a: torch.as_tensor(a).clone().pin_memory()          # noqa: E731
+    hx, hX, hU = pin(xref), pin(np.full_like(X0, np.nan)), pin(np.full_like(U0, np.nan))
+    n0 = opt.handle.launch_count
+    Uz, Xz, stz, itz = opt.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
+    assert opt.handle.launch_count - n0 == 1                          # one launch, no chunking
+    assert np.array_equal(Uz, Ua) and np.array_equal(Xz, Xa) and np.array_equal(stz, sta) and np.array_equal(itz, ita)
+    # warm start through pinned buffers, separate in / out arrays: one further iteration or so, same as the device path
+    hXi, hUi = pin(Xa), pin(Ua)
+    hX.fill_(float("nan")); hU.fill_(float("nan"))
+    Uw, Xw, stw, itw = opt.solve_batch_host(hx.numpy(), hXi.numpy(), hUi.numpy(), out=(hX.numpy(), hU.numpy()))
+    Ub, Xb, stb, itb = _np(*opt.solve_batch(xref, Xa, Ua))
+    assert np.array_equal(Uw, Ub) and np.array_equal(Xw, Xb) and np.array_equal(itw, itb)
+    assert np.array_equal(hXi.numpy(), Xa) and np.array_equal(hUi.numpy(), Ua)          # inputs untouched
+    # in place
+    Ui, Xi, sti, iti = opt.solve_batch_host(hx.numpy(), hXi.numpy(), hUi.numpy(), inplace=True)
+    assert np.array_equal(Ui, Ub) and np.array_equal(Xi, Xb)
+    # staged route forced / pageable buffers
+    monkeypatch.setenv("MPCB200_HOST_STAGED", "1")
+    n0 = opt.handle.launch_count
+    Us, Xs, sts, its = opt.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
+    assert opt.handle.launch_count - n0 >= 1
+    assert np.array_equal(Us, Ua) and np.array_equal(Xs, Xa) and np.array_equal(sts, sta)
+    monkeypatch.delenv("MPCB200_HOST_STAGED")
+    Up, Xp, stp, itp = opt.solve_batch_host(xref)                     # pageable numpy arrays -> staged
+    assert np.array_equal(Up, Ua) and np.array_equal(Xp, Xa) and np.array_equal(itp, ita)
