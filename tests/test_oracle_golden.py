@@ -167,3 +167,39 @@ def test_reference_window_rule_q8():
     assert np.all(w[1:, 0] == np.arange(60, 70))
     w30 = nlp.reference_window(0, x, 30, 30, path[:30], orient[:30], 7.0)   # N == T: path[0:30] at every step
     assert np.all(w30[1:, 0] == np.arange(0, 30))
+
+
+@pytest.mark.parametrize("key,name,sigma", [("casadi_zam_lf", "ZAM_Over-1_1_LF", 0.1), ("casadi_zam_ca", "ZAM_Over-1_1_CA", 0.05)])
+def test_recorded_ipopt_controls_pin_the_oracle_optimum_statistically(key, name, sigma):
+    """SURVEY 8c (6), extended to every recorded step.  The reference's recorded CasADi/IPOPT closed loops (N = 10,
+    /root/reference/test/2D_plots_casadi_ZAM_Over-1_1_*/) applied u = u*_0 + N(0, sigma^2) (optimizer.py:611-617) at the
+    recorded state x_k.  Re-solving the restated NLP at every recorded (x_k, window k) must therefore leave residuals
+    u_rec - u*_0(oracle) that look like that noise: zero median within its standard error, robust spread = sigma.
+    A wrong cost pairing (Q2), a terminal cost (Q1), a wrong window (Q8) or friction row (Q3) shifts u*_0 by far more.
+    A few steps are outliers in the RECORDING (IPOPT's return status is never checked, optimizer.py:607-609), so the
+    statistics are robust ones.  (The Lanker run is not used: its route-planner path is only approximately restated.)"""
+    import mpc_b200
+    from oracle import ipm
+    g = np.load(os.path.join(G, "recorded_runs.npz"))
+    sc = mpc_b200.load_scenario(name)
+    Xr, Ur = g[key + "_x"], g[key + "_u"]
+    N, T = 10, sc.iter_length
+    res = []
+    for i, x in enumerate(Xr):
+        xref = np.tile(x, (N + 1, 1)) if i == 0 else nlp.reference_window(i - 1, x, N, T, sc.reference_path, sc.orientation,
+                                                                          sc.desired_velocity)
+        d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref, sc.static_obstacle)
+        r = ipm.solve(d, nlp.pack(np.zeros((N, 2)), np.tile(x, (N + 1, 1))))
+        if r["status"] == 1:
+            res.append(Ur[i] - nlp.split(r["w"], N)[0][0])
+    res = np.array(res)
+    assert len(res) >= len(Xr) - 2
+    se = sigma / np.sqrt(len(res))
+    for c in range(2):
+        e = res[:, c]
+        inl = np.abs(e) < 4 * sigma
+        assert inl.mean() >= 0.85                                              # at most a few recording outliers
+        assert abs(np.median(e)) < 4 * 1.2533 * se                             # median of n normals: se * sqrt(pi/2)
+        assert abs(e[inl].mean()) < 4 * se
+        mad_sigma = 1.4826 * np.median(np.abs(e - np.median(e)))
+        assert 0.5 * sigma < mad_sigma < 1.5 * sigma
