@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCB200_ABI_VERSION 2
+#define MPCB200_ABI_VERSION 3
 
 enum { MPCB200_F32 = 0, MPCB200_F64 = 1 };
 enum { MPCB200_HESS_GAUSS_NEWTON = 0, MPCB200_HESS_EXACT = 1 };
@@ -64,6 +64,7 @@ typedef struct mpcb200_config {
   double tau_min, bound_push;      /* fraction-to-the-boundary, initial interior push */
   double mu_min_alpha;             /* mu is reduced only after an accepted step length >= this */
   double mu_up_alpha, mu_up_factor, mu_max;   /* barrier warm-up: mu *= mu_up_factor (<= mu_max) while the first steps are blocked below mu_up_alpha */
+  double mu_factor_full;           /* barrier reduction factor after a FULL primal and dual step (alpha = 1): <= mu_factor */
   double kappa_sigma;              /* multipliers kept within [mu/(kappa s), kappa mu/s] (IPOPT kappa_sigma) */
   double screen_inv_curv;          /* obstacle rows whose barrier curvature mu/s^2 is below 1/this are skipped for the iteration (<= 0: keep all) */
   double trust_step;               /* feasible iterate + step below this: the Newton step is accepted without the merit test */

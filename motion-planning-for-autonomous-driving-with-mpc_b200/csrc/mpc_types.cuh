@@ -41,6 +41,7 @@ struct ParamsT {
   int stall_iters;               // stall exit after this many iterations at mu_min without halving the step
   T mu_min_alpha;                // the barrier parameter is reduced only after a step of at least this length
   T mu_up_alpha, mu_up_factor, mu_max;   // barrier warm-up: raise mu while the first steps are blocked below mu_up_alpha
+  T mu_factor_full;                      // barrier reduction factor after a full (alpha = 1) primal and dual step
   T kappa_sigma;                 // multipliers are kept within [mu/(kappa s), kappa mu/s] after every step
   int init_rollout;              // 1: initial states = Euler rollout of the initial controls from the pinned state
 };

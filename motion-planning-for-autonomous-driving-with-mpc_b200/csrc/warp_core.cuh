@@ -936,7 +936,9 @@ struct WarpSolver {
     }
     if (al >= P.mu_min_alpha) {
       // monotone barrier update, linear (mu_factor) far out and superlinear (avg^1.5, as IPOPT's theta_mu) close in
-      const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(P.mu_factor * avg, avg * m_sqrt(avg))));
+      // (a full primal and dual step means the linearisation was trusted all the way: reduce faster)
+      const T fac = (al >= T(1) && f.a_d >= T(1)) ? P.mu_factor_full : P.mu_factor;
+      const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(fac * avg, avg * m_sqrt(avg))));
       if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
       st.mu = mu_new;
     }

@@ -256,9 +256,9 @@ class B200Optimizer(_Base):
         status = np.empty(B, np.int32)
         iters = np.empty(B, np.int32)
         h = self.handle
-        h.check(h.lib.mpcb200_solve_host(h.h, xref.ctypes.data, X_in.ctypes.data if not cold else None,
-                                         U_in.ctypes.data if not cold else None, X.ctypes.data, U.ctypes.data,
-                                         status.ctypes.data, iters.ctypes.data, B))
+        ptr = lambda a: a.__array_interface__["data"][0]          # noqa: E731  (a.ctypes.data builds a ctypes object per call)
+        h.check(h.lib.mpcb200_solve_host(h.h, ptr(xref), ptr(X_in) if not cold else None, ptr(U_in) if not cold else None,
+                                         ptr(X), ptr(U), ptr(status), ptr(iters), B))
         return U, X, status, iters
 
     def plant_step_shift(self, x, U, X):

@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_matches_header_layout():
     from mpc_b200 import _capi
     cfg = _capi.default_config(30, _capi.F32)
-    assert cfg.abi_version == _capi.ABI_VERSION == 2 and cfg.N == 30
-    assert C.sizeof(_capi.Config) == 8 * 4 + 8 * (3 + 5 + 2 + 7 + 2 + 6 + 7 + 8) + 4 * 4
+    assert cfg.abi_version == _capi.ABI_VERSION == 3 and cfg.N == 30
+    assert C.sizeof(_capi.Config) == 8 * 4 + 8 * (3 + 5 + 2 + 7 + 2 + 6 + 7 + 9) + 4 * 4
     assert abs(cfg.l_wb - 2.5789128) < 1e-12 and cfg.l_fric == 2.578
     assert (cfg.deltav_min, cfg.deltav_max, cfg.a_max, cfg.v_min, cfg.v_max) == (-0.4, 0.4, 11.5, 0.0, 50.8)
     c64 = _capi.default_config(50, _capi.F64)
