@@ -106,45 +106,59 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region.  The region lasts only tens of milliseconds, far below the
+    start-up time of an `nvidia-smi -lms` child, so the samples come from NVML in-process (pynvml, a thread polling every
+    ~2 ms; NVML queries are host-side and do not enter the CUDA stream).  Falls back to one `nvidia-smi` query."""
+    BAD = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.p = index, [], None
+        self.index, self.sm, self.mask, self.stop_flag, self.t, self.h, self.nv = index, [], 0, False, None, None, None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it holds plain ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.p = None
+            self.nv = None
 
-    def _read(self):
-        for ln in self.p.stdout:
-            self.rows.append(ln.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
+        if self.nv is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            reasons = sorted(n for n, bit in self.BAD if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(self.sm), "source": "NVML in-process, 2 ms poll over the timed regions"}
         try:
-            self.p.wait(timeout=5)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            reasons = sorted(n for (n, _), v in zip(self.BAD, f[2:6]) if v.lower().startswith("active"))
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": reasons, "samples": 1,
+                    "source": "nvidia-smi, one query right after the timed regions"}
         except Exception:
-            self.p.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------------ product arm
