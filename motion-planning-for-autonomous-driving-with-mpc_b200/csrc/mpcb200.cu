@@ -107,7 +107,7 @@ __device__ __forceinline__ bool tile_is_bulk(int nvalid, int per_problem) {
 // ===================================================================================================== solve kernel
 // One warp per ego instance; WPC warps (problems) per CTA.  All SQP iterations of a problem run inside the launch
 // (MODE_ONESHOT), or `n_iter` of them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
-template <typename T, int WPC>
+template <typename T, int WPC, int HM>
 __global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   __shared__ __align__(8) uint64_t bar_io;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(cons
 
   const WarpCtx w;
   T obs[6];
-  WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
+  WarpSolver<T, HM> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   const bool need_xref = (a.mode != MODE_ITER);
   const bool need_init = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
@@ -261,7 +261,7 @@ __device__ __forceinline__ void ref_window_rows(int i, int N, int Tlen, const do
 
 // The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631) for one ego per warp, no host
 // round trip between MPC steps: solve, record u_0, plant step + warm-start shift, next reference window.
-template <typename T, int WPC>
+template <typename T, int WPC, int HM>
 __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __grid_constant__ LoopArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __
   double* my_U = sm.U(wid);
   const WarpCtx w;
   T obs[6];
-  WarpSolver<T> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
+  WarpSolver<T, HM> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
   ProbState<T> st;
   double x[5];
   for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
@@ -381,44 +381,47 @@ static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
 
-template <typename T, int WPC>
+template <typename T, int WPC, int HM>
 static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s, size_t smem) {
   const int ctas = (a.B + WPC - 1) / WPC;
-  mpc_warp_solve_kernel<T, WPC><<<ctas, 32 * WPC, smem, s>>>(a);
+  mpc_warp_solve_kernel<T, WPC, HM><<<ctas, 32 * WPC, smem, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
-template <typename T, int WPC>
+template <typename T, int WPC, int HM>
 static cudaError_t launch_loop(mpcb200_handle* h, const LoopArgs<T>& a, cudaStream_t s) {
   const int ctas = (a.B + WPC - 1) / WPC;
-  mpc_warp_closed_loop_kernel<T, WPC><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
+  mpc_warp_closed_loop_kernel<T, WPC, HM><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
 
+// kernel instantiations: arithmetic type x problems per CTA (2, or 1 when the slab of a long horizon leaves no room for
+// two) x Hessian mode
 template <typename T>
 static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s, int wpc, size_t smem) {
-  if (wpc == 4) return launch_solve<T, 4>(h, a, s, smem);
-  if (wpc == 2) return launch_solve<T, 2>(h, a, s, smem);
-  return launch_solve<T, 1>(h, a, s, smem);
+  const bool ex = a.P.hessian == HESS_EXACT;
+  if (wpc == 2) return ex ? launch_solve<T, 2, HESS_EXACT>(h, a, s, smem) : launch_solve<T, 2, HESS_GN>(h, a, s, smem);
+  return ex ? launch_solve<T, 1, HESS_EXACT>(h, a, s, smem) : launch_solve<T, 1, HESS_GN>(h, a, s, smem);
 }
 template <typename T>
 static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t s) {
-  if (h->wpc == 4) return launch_loop<T, 4>(h, a, s);
-  if (h->wpc == 2) return launch_loop<T, 2>(h, a, s);
-  return launch_loop<T, 1>(h, a, s);
+  const bool ex = a.P.hessian == HESS_EXACT;
+  if (h->wpc == 2) return ex ? launch_loop<T, 2, HESS_EXACT>(h, a, s) : launch_loop<T, 2, HESS_GN>(h, a, s);
+  return ex ? launch_loop<T, 1, HESS_EXACT>(h, a, s) : launch_loop<T, 1, HESS_GN>(h, a, s);
 }
 
 // opt the handle's kernel instantiations in to their dynamic shared memory size (once, at create)
 template <typename T, int WPC>
 static cudaError_t configure_kernels_t(size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC, HESS_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC, HESS_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC, HESS_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC, HESS_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return e;
 }
 template <typename T>
 static cudaError_t configure_kernels(int wpc, size_t smem) {
-  if (wpc == 4) return configure_kernels_t<T, 4>(smem);
   if (wpc == 2) return configure_kernels_t<T, 2>(smem);
   return configure_kernels_t<T, 1>(smem);
 }
@@ -499,7 +502,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   const size_t reserve = 1024;
   h->wpc = 0;
   int wpc_pref = 2;
-  if (const char* ev = getenv("MPCB200_WPC")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) wpc_pref = v; }   // tuning knob
+  if (const char* ev = getenv("MPCB200_WPC")) { const int v = atoi(ev); if (v == 1 || v == 2) wpc_pref = v; }   // tuning knob
   for (int wpc : {wpc_pref, 2, 1}) {
     const size_t need = smem_bytes_for(cfg->N, L.words, h->elem, wpc);
     if (need + reserve <= smem_max) { h->wpc = wpc; h->smem_bytes = need; break; }

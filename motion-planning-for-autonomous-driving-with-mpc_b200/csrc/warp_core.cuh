@@ -148,7 +148,11 @@ struct SlabRef {
 };
 #endif
 
-template <typename T>
+// HM: Hessian mode fixed at compile time (HESS_GN / HESS_EXACT: the kernels, so that a Gauss-Newton kernel carries no
+// exact-Hessian code between its hot phases -- instruction-cache footprint) or HESS_RUNTIME (P.hessian decides: the
+// host emulator).
+enum : int { HESS_RUNTIME = -1 };
+template <typename T, int HM = HESS_RUNTIME>
 struct WarpSolver {
   const ParamsT<T>& P;
   const WLayout L;
@@ -516,7 +520,12 @@ struct WarpSolver {
     w.sync();
     return ok;
   }
-  MPC_HD bool backward(int hess) const { return hess == HESS_EXACT ? backward_t<HESS_EXACT>() : backward_t<HESS_GN>(); }
+  // factor + solve with the configured Hessian; an indefinite exact-Hessian control block falls back to Gauss-Newton
+  MPC_HD void backward() const {
+    if (HM == HESS_GN) { backward_t<HESS_GN>(); return; }
+    if (HM == HESS_EXACT || P.hessian == HESS_EXACT) { if (backward_t<HESS_EXACT>()) return; }
+    backward_t<HESS_GN>();
+  }
 
   // ---------------------------------------------------------------- phase D: forward sweep (lane = state component)
   // dx_{k+1} = A dx_k + B du_k + d_k with du_k = kff + K dx_k: lane r < 5 owns component r.  Rows 0, 1, 4 take their
@@ -852,7 +861,7 @@ struct WarpSolver {
   MPC_HD void iterate(ProbState<T>& st) const {
     if (st.done) return;
     linearize(st);
-    if (!backward(P.hessian)) backward(HESS_GN);
+    backward();
     forward_sweep();
     FwdOut f = forward_stats(st);
     if (!m_finite(f.step_inf) || !m_finite(f.dphi)) { st.status = ST_NAN; st.done = 1; return; }
