@@ -3,7 +3,7 @@
 
 One "step" = one pass of the hot path over one batch: `mpcb200_solve` (ONE fused kernel launch that runs every SQP
 iteration of its 1024 NLPs) on inputs already resident in HBM.  `value` = solves/s over all ranks (weak scaling: every
-rank owns its own 1024 instances, no data-path collective).  `e2e` = the same metric through the public host-buffer call
+rank owns its own copy of the seeded 1024-instance batch, no data-path collective).  `e2e` = the same metric through the public host-buffer call
 `B200Optimizer.solve_batch_host` (pinned host arrays, H2D + solve + D2H inside the timed region).
 
   python bench.py [--gpus N --steps K --warmup W]          product arm (N>1 under torchrun, one rank per GPU)
@@ -173,6 +173,9 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # stdout carries exactly ONE line (the JSON): keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local))
@@ -181,8 +184,10 @@ def run_product(args):
         local = 0
     dev = torch.device("cuda", local)
     N, B = N_HORIZON, BATCH
-    # weak scaling: every rank owns B instances of its own (seed + rank); no data-path collective
-    sc, x0, xref, X0, U0 = mpc_b200.make_batch(SCENARIO, B, N, SEED + rank)
+    # weak scaling: every rank owns its own copy of the seeded config-2 batch (seed 20261017), so the per-GPU work
+    # is EXACTLY the same at every N (with per-rank seeds the slowest draw -- the instance with the most SQP iterations --
+    # would set the max-over-ranks time and read as a scaling loss); no data-path collective
+    sc, x0, xref, X0, U0 = mpc_b200.make_batch(SCENARIO, B, N, SEED)
     opt = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=args.precision,
                         hessian=args.hessian, max_batch=B, device=local)
     f64 = torch.float64
@@ -284,7 +289,7 @@ def run_product(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "p50_ms_per_step": float(np.median(ms)), "p50_ms_per_solve": float(np.median(ms)) / B,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"{SCENARIO} batch={B} perturbed x0 (seed {SEED}+rank) N={N} cold start (BASELINE configs[1])",
+        "config": {"workload": f"{SCENARIO} batch={B} perturbed x0 (seed {SEED}) N={N} cold start (BASELINE configs[1]); every rank solves its own copy",
                    "parallelism": f"batch-shard x{world} (independent NLPs, no data-path collective)",
                    "l2": "256 MB flush write between timed iterations", "hessian": args.hessian,
                    "converged": f"{n_ok}/{B}", "mean_sqp_iters": float(iters.mean()), "max_sqp_iters": int(iters.max())},
