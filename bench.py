@@ -44,7 +44,7 @@ def _oracle_one(args):
     sc = mpc_b200.load_scenario(name)
     d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref, sc.static_obstacle)
     r = ipm.solve(d, nlp.pack(U, X))
-    return r["status"], r["iters"]
+    return r["status"], r["iters"], r["w"]
 
 
 def cpu_oracle_rate(n_sample, cores, pool=None):
@@ -62,8 +62,8 @@ def cpu_oracle_rate(n_sample, cores, pool=None):
     dt = time.perf_counter() - t0
     if own:
         pool.close()
-    ok = sum(1 for s, _ in res if s == 1)
-    return n_sample / dt, dt, ok
+    ok = sum(1 for r in res if r[0] == 1)
+    return n_sample / dt, dt, ok, res
 
 
 def run_reference(args):
@@ -277,12 +277,25 @@ def run_product(args):
         pass
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only at N=1
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_sample = BATCH                                   # the whole workload: ~25 ms per solve per core, 10-40 core-seconds
-        rate, dt, ok = cpu_oracle_rate(n_sample, cores)
+        rate, dt, ok, ores = cpu_oracle_rate(n_sample, cores)
         cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                "sample": f"first {n_sample} of the {BATCH} instances, float64 oracle (oracle/ipm.py), Pool({cores}), {dt:.1f} s, {ok} converged"}
+        # the oracle solutions of that leg double as the checker of the timed GPU results (same instances, same cold start)
+        from oracle import nlp as _nlp
+        Xg, Ug = d_X.cpu().numpy(), d_U.cpu().numpy()
+        dU = dX = 0.0
+        n_cmp = 0
+        for b, (st_o, _, w_o) in enumerate(ores):
+            if st_o == 1 and status[b] == 1:
+                Uo, Xo = _nlp.split(w_o, N)
+                dU = max(dU, float(np.abs(Uo - Ug[b]).max())); dX = max(dX, float(np.abs(Xo - Xg[b]).max()))
+                n_cmp += 1
+        parity = {"checked": n_cmp, "of": B, "max_abs_dU": dU, "max_abs_dX": dX, "tolerance": 1e-3,
+                  "against": "float64 oracle (restated reference NLP), every instance of the timed batch"}
     nx, nu = 5 * (N + 1), 2 * N
     line = {
         "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "solves/s", "n_gpus": world,
@@ -302,6 +315,7 @@ def run_product(args):
                      "note": "algorithmic bytes = sum over problems of SQP iterations x 4(219N+65) B (KKT slab staged once per iteration); "
                              "the fused kernel keeps the slab in shared memory, so real DRAM traffic is far below this"},
         "cpu_baseline": cpu,
+        "parity": parity,
         "clocks": clocks,
     }
     print(json.dumps(line))

@@ -230,6 +230,14 @@ class B200Optimizer(_Base):
         h.check(h.lib.mpcb200_sqp_end(h.h, X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), s))
         return U, X, status, iters
 
+    def alloc_host_buffers(self, B):
+        """Pinned host arrays for `solve_batch_host`'s zero-copy route: numpy views (xref [B,N+1,5], X [B,N+1,5], U [B,N,2],
+        float64) of page-locked torch tensors the device can address; fill `xref` in place, pass `out=(X, U)`.
+        The tensors are kept alive by the returned arrays (`.base`)."""
+        t = self.torch
+        mk = lambda *shape: t.empty(*shape, dtype=t.float64).pin_memory().numpy()          # noqa: E731
+        return mk(B, self.N + 1, 5), mk(B, self.N + 1, 5), mk(B, self.N, 2)
+
     def solve_batch_host(self, xref, X_init=None, U_init=None, inplace=False, out=None):
         """End-to-end call with HOST numpy buffers (H2D + solve + D2H inside the library, synchronous).
         X_init = U_init = None: cold start (the reference's step-0 guess), only xref is uploaded.
