@@ -188,8 +188,12 @@ def run_product(args):
     # is EXACTLY the same at every N (with per-rank seeds the slowest draw -- the instance with the most SQP iterations --
     # would set the max-over-ranks time and read as a scaling loss); no data-path collective
     sc, x0, xref, X0, U0 = mpc_b200.make_batch(SCENARIO, B, N, SEED)
+    solver_opts = {}
+    for kv in args.opt:                                   # tuning knob: fields of mpcb200_config, e.g. --opt mu_min=1e-6
+        k, v = kv.split("=")
+        solver_opts[k] = int(v) if k in ("max_iter", "ls_max", "acc_iters", "stall_iters", "refine_f64", "init_rollout") else float(v)
     opt = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=args.precision,
-                        hessian=args.hessian, max_batch=B, device=local)
+                        hessian=args.hessian, max_batch=B, device=local, **solver_opts)
     f64 = torch.float64
     d_xref = torch.as_tensor(xref, device=dev)
     assert np.array_equal(X0, np.repeat(xref[:, :1], N + 1, axis=1)) and not U0.any()      # the workload IS the cold start
@@ -304,7 +308,7 @@ def run_product(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"{SCENARIO} batch={B} perturbed x0 (seed {SEED}) N={N} cold start (BASELINE configs[1]); every rank solves its own copy",
                    "parallelism": f"batch-shard x{world} (independent NLPs, no data-path collective)",
-                   "l2": "256 MB flush write between timed iterations", "hessian": args.hessian,
+                   "l2": "256 MB flush write between timed iterations", "hessian": args.hessian, **({"solver_opts": solver_opts} if solver_opts else {}),
                    "converged": f"{n_ok}/{B}", "mean_sqp_iters": float(iters.mean()), "max_sqp_iters": int(iters.max())},
         "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": B * nx * 8,
                 "d2h_bytes_per_step": B * (nx + nu) * 8 + B * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -332,6 +336,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--hessian", default="gn", choices=["exact", "gn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments; default: none)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

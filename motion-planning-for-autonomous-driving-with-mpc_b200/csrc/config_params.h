@@ -36,7 +36,7 @@ inline void default_config(mpcb200_config* c, int N, int precision) {
   for (int i = 0; i < 6; ++i) c->obstacle[i] = ob[i];
   c->mu0 = 0.01; c->mu_factor = 0.2; c->tau_min = 0.99; c->bound_push = 1e-2;
   if (precision == MPCB200_F64) { c->mu_min = 1e-9; c->tol_step = 1e-8; c->tol_feas = 1e-8; c->acc_factor = 1000.0; }
-  else                          { c->mu_min = 1e-6; c->tol_step = 2e-5; c->tol_feas = 1e-4; c->acc_factor = 5.0; }
+  else                          { c->mu_min = 1e-7; c->tol_step = 2e-5; c->tol_feas = 1e-4; c->acc_factor = 5.0; }   // mu_min: a weakly active row ends s ~ sqrt(mu_min / h) inside its bound (5e-4 at h = 0.4; 1.6e-3 at 1e-6)
   c->acc_iters = 4; c->stall_iters = 10; c->refine_f64 = 0; c->trust_step = 1e-2; c->screen_inv_curv = 1e6; c->init_rollout = 0; c->kappa_sigma = 1e10; c->mu_min_alpha = 0.5;
   c->mu_up_alpha = 0.5; c->mu_up_factor = 10.0; c->mu_max = 1e3; c->mu_factor_full = 0.04;
 }
