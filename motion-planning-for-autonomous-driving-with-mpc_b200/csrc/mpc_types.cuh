@@ -105,6 +105,16 @@ MPC_HD float m_rsqrt(float x) {
 #endif
 }
 MPC_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+// natural log by one MUFU op (lg2.approx: absolute error ~1e-7 for arguments near 1); callers add the first-order
+// correction for the rounding of the argument themselves (trial_merit)
+MPC_HD float m_fastlog(float u) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u)); return r * 0.69314718056f;
+#else
+  return logf(u);
+#endif
+}
+MPC_HD double m_fastlog(double u) { return log(u); }
 MPC_HD float m_eps(float) { return 6e-8f; }
 MPC_HD double m_eps(double) { return 1.2e-16; }
 // |r| with a dead zone at the rounding level of the distance h it was computed from: the slack residual of a far,

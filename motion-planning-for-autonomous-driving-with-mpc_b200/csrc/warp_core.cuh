@@ -770,19 +770,25 @@ struct WarpSolver {
       }
       if (k == 0) rts[10] = du1 * m_rcp(m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side
       }   // act
-      bool small = true;
-#pragma unroll
-      for (int i = 0; i < 12; ++i) { small = small && (m_abs(rts[i]) < T(0.02)); ok = ok && (rts[i] > T(-1)); }
-      if (sizeof(T) == 4 && w.all(small)) {      // float only: the series is good to ~3e-8 relative
+      if (sizeof(T) == 4) {
+        // float: branch-free per ratio -- a 4-term series below 0.02 (relative error < x^4/5 = 3e-8), otherwise one MUFU
+        // logarithm of u = 1 + x with the first-order correction (x - (u - 1)) / u for the rounding of u (relative error
+        // < 1e-5 there, on terms whose merit change is orders of magnitude above that).  12 log1pf calls were ~400
+        // instructions of the per-iteration instruction stream.
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-          const T x = rts[i];
-          const T l = x * (T(1) + x * (T(-0.5) + x * (T(1) / T(3) - T(0.25) * x)));     // log1p(x), |x| < 0.02: rel. error < x^4/5 = 3e-8
+          ok = ok && (rts[i] > T(-1));
+          const T x = m_max(rts[i], T(-0.999999));
+          const T ser = x * (T(1) + x * (T(-0.5) + x * (T(1) / T(3) - T(0.25) * x)));
+          const T u = T(1) + x;
+          const T big = m_fastlog(u) + (x - (u - T(1))) * m_rcp(u);
+          const T l = (m_abs(x) < T(0.02)) ? ser : big;
           lg += l; lga += m_abs(l);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
+          ok = ok && (rts[i] > T(-1));
           const T l = m_log1p(m_max(rts[i], T(-0.999999)));
           lg += l; lga += m_abs(l);
         }
