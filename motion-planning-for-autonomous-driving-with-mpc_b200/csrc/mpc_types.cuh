@@ -116,6 +116,9 @@ MPC_HD float m_rsqrt(float x) {
 #endif
 }
 MPC_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+// square root where a few ulp do not matter (thresholds, the barrier schedule): x * rsqrt(x), no IEEE slow path
+MPC_HD float m_sqrt_fast(float x) { const float y = fmaxf(x, 1e-30f); return y * m_rsqrt(y); }
+MPC_HD double m_sqrt_fast(double x) { return sqrt(x); }
 // natural log by one MUFU op (lg2.approx: absolute error ~1e-7 for arguments near 1); callers add the first-order
 // correction for the rounding of the argument themselves (trial_merit)
 MPC_HD float m_fastlog(float u) {

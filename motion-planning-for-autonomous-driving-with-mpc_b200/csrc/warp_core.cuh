@@ -162,9 +162,12 @@ struct WarpSolver {
   const int lane;
   const LaneTab tb;
   const T il_wb;     // 1 / wheelbase
+  const T idt_;      // 1 / dt
+  const T irows;     // 1 / (number of inequality rows) = 1 / (10 N + 1)
 
   MPC_HD WarpSolver(const ParamsT<T>& P_, const SlabRef<T>& slab, const T* obs_, const WarpCtx& w_)
-      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()), il_wb(T(1) / P_.l_wb) {}
+      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()), il_wb(T(1) / P_.l_wb), idt_(T(1) / P_.dt),
+        irows(T(1) / T(10 * P_.N + 1)) {}
 
   MPC_HD T& sx(int k, int f) const { return sl[L.o_state + ST_STRIDE * k + f]; }
   MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + REC_STRIDE * k + f]; }
@@ -196,9 +199,9 @@ struct WarpSolver {
   // distance: every circle pair is at least (centre distance - obs_spread - ego_off) apart.
   MPC_HD T far_threshold2(T mu) const {
     if (!(P.screen_inv_curv > T(0))) return T(3e38);       // screening off
-    const T sp1 = m_sqrt((obs[2] - obs[0]) * (obs[2] - obs[0]) + (obs[3] - obs[1]) * (obs[3] - obs[1]));
-    const T sp2 = m_sqrt((obs[4] - obs[0]) * (obs[4] - obs[0]) + (obs[5] - obs[1]) * (obs[5] - obs[1]));
-    const T reach = P.r_sum + P.ego_off + m_max(sp1, sp2) + m_sqrt(mu * P.screen_inv_curv);
+    const T sp1 = m_sqrt_fast((obs[2] - obs[0]) * (obs[2] - obs[0]) + (obs[3] - obs[1]) * (obs[3] - obs[1]));
+    const T sp2 = m_sqrt_fast((obs[4] - obs[0]) * (obs[4] - obs[0]) + (obs[5] - obs[1]) * (obs[5] - obs[1]));
+    const T reach = P.r_sum + P.ego_off + m_max(sp1, sp2) + m_sqrt_fast(mu * P.screen_inv_curv);
     return reach * reach;
   }
   MPC_HD bool is_far(T px, T py, T thr2) const {
@@ -342,7 +345,7 @@ struct WarpSolver {
   // ---------------------------------------------------------------- phase A: stage KKT blocks (lane = stage)
   MPC_HD void linearize(const ProbState<T>& st) const {
     const int N = P.N;
-    const T dt = P.dt, mu = st.mu, idt = T(1) / P.dt;
+    const T dt = P.dt, mu = st.mu, idt = idt_;
     const T thr2 = far_threshold2(mu);
     for (int k = lane; k < N; k += 32) {
       T x0d[5], x1d[5], x1a[5];
@@ -534,7 +537,7 @@ struct WarpSolver {
   struct FwdCoef { T f0, f1, f2, f3, f4, fc, d; };
   MPC_HD void forward_sweep() const {
     const int N = P.N;
-    const T idt = T(1) / P.dt;
+    const T idt = idt_;
     const int row = lane < 5 ? lane : 0;
     T dx0 = T(0), dx1 = T(0), dx2 = T(0), dx3 = T(0), dx4 = T(0), mine = T(0);
     const T* pf0 = &sl[L.o_rec + tb.fc[0]]; const T* pf1 = &sl[L.o_rec + tb.fc[1]]; const T* pf2 = &sl[L.o_rec + tb.fc[2]];
@@ -637,8 +640,8 @@ struct WarpSolver {
       o.blk = code; }
 #endif
     o.a_p = w.max_nonneg(m_max(o.a_p, T(0))); o.a_d = w.max_nonneg(m_max(o.a_d, T(0)));
-    o.a_p = (o.a_p > tau) ? tau / o.a_p : T(1);
-    o.a_d = (o.a_d > tau) ? tau / o.a_d : T(1);
+    o.a_p = (o.a_p > tau) ? tau * m_rcp(o.a_p) : T(1);
+    o.a_d = (o.a_d > tau) ? tau * m_rcp(o.a_d) : T(1);
     o.step_inf = w.max_nonneg(fin ? o.step_inf : T(0));
     o.dphi = w.sum(o.dphi); o.c1 = w.sum(o.c1); o.mag = w.sum(o.mag);
     if (!allfin) o.step_inf = T(NAN);     // the caller turns this into ST_NAN
@@ -804,7 +807,7 @@ struct WarpSolver {
   // ---------------------------------------------------------------- phase G: commit the step + complementarity statistics
   MPC_HD void commit(ProbState<T>& st, T al, T ad, T& avg, T& cmax) const {
     const int N = P.N;
-    const T mu = st.mu, ikap = T(1) / P.kappa_sigma;
+    const T mu = st.mu, ikap = m_rcp(P.kappa_sigma);
     T sum = T(0); cmax = T(0);
     for (int k = lane; k < N; k += 32) {
       const T u0 = rc(k, R_U), u1 = rc(k, R_U + 1);
@@ -859,7 +862,7 @@ struct WarpSolver {
     }
     sum = w.sum(sum);
     cmax = w.max_nonneg(m_max(cmax, T(0)));
-    avg = sum / T(10 * N + 1);
+    avg = sum * irows;
     w.sync();
   }
 
@@ -875,7 +878,7 @@ struct WarpSolver {
     // a noise-level c1 would blow rho up and hand the line search to the noise)
     const T epsm = m_eps(T(0));
     if (f.c1 > T(8) * epsm * f.mag) {
-      const T need = f.dphi / (T(0.5) * f.c1);
+      const T need = f.dphi * m_rcp(T(0.5) * f.c1);
       if (need > st.rho) st.rho = need * T(1.5) + T(1);
     }
     const T slope = f.dphi - st.rho * f.c1;
@@ -953,7 +956,7 @@ struct WarpSolver {
       // monotone barrier update, linear (mu_factor) far out and superlinear (avg^1.5, as IPOPT's theta_mu) close in
       // (a full primal and dual step means the linearisation was trusted all the way: reduce faster)
       const T fac = (al >= T(1) && f.a_d >= T(1)) ? P.mu_factor_full : P.mu_factor;
-      const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(fac * avg, avg * m_sqrt(avg))));
+      const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(fac * avg, avg * m_sqrt_fast(avg))));
       if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
       st.mu = mu_new;
     }
