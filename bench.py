@@ -173,9 +173,9 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
-        # stdout carries exactly ONE line (the JSON): keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly ONE line (the JSON): NCCL's debug output ("NCCL version ..." banner at NCCL_DEBUG=VERSION /
+        # WARN, which the box sets) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local))
