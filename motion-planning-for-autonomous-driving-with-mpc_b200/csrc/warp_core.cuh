@@ -41,7 +41,7 @@ enum : int {
   R_ONE = 30,   // 1  constant 1
   R_H = 31,     // 8  Hessian of the x_{k+1} terms: h00 h01 h04 h11 h14 h44 h22 h33
   R_GX = 39,    // 5  gradient of the x_{k+1} terms (barrier gradient at the current mu)
-  R_RU = 44,    // 4  Ru0 Ru1 ru0/dt ru1/dt (control Hessian diagonal / gradient incl. barrier terms)
+  R_RU = 44,    // 4  Ru0/dt^2 Ru1/dt^2 ru0/dt ru1/dt (control Hessian diagonal / gradient incl. barrier terms, pre-scaled for the sweep)
   R_LC = 48,    // 5  multiplier-weighted gradient of the x_{k+1} terms (adjoint recursion, exact Hessian)
   R_KK = 53,    // 12 gains times dt: dt*(K0[0..4] k0 K1[0..4] k1)
   R_DX = 65,    // 5  step dx_{k+1}
@@ -319,14 +319,14 @@ struct WarpSolver {
       const T vv = m_min(m_max(xa(k + 1, 3), P.v_min + pv), P.v_max - pv);
       sx(k + 1, S_XT + 2) = de - sx(k + 1, S_XR + 2);
       sx(k + 1, S_XT + 3) = vv - sx(k + 1, S_XR + 3);
-      rc(k, R_V + V_DD_LO) = mu / (dd - P.dd_min);
-      rc(k, R_V + V_DD_HI) = mu / (P.dd_max - dd);
-      rc(k, R_V + V_A_HI) = mu / (ahi - a);
-      rc(k, R_V + V_A_LO) = (k == 0) ? mu / (a - st.a0_lo) : T(0);
-      rc(k, R_V + V_DE_LO) = mu / (de - P.de_min);
-      rc(k, R_V + V_DE_HI) = mu / (P.de_max - de);
-      rc(k, R_V + V_V_LO) = mu / (vv - P.v_min);
-      rc(k, R_V + V_V_HI) = mu / (P.v_max - vv);
+      rc(k, R_V + V_DD_LO) = mu * m_rcp(dd - P.dd_min);
+      rc(k, R_V + V_DD_HI) = mu * m_rcp(P.dd_max - dd);
+      rc(k, R_V + V_A_HI) = mu * m_rcp(ahi - a);
+      rc(k, R_V + V_A_LO) = (k == 0) ? mu * m_rcp(a - st.a0_lo) : T(0);
+      rc(k, R_V + V_DE_LO) = mu * m_rcp(de - P.de_min);
+      rc(k, R_V + V_DE_HI) = mu * m_rcp(P.de_max - de);
+      rc(k, R_V + V_V_LO) = mu * m_rcp(vv - P.v_min);
+      rc(k, R_V + V_V_HI) = mu * m_rcp(P.v_max - vv);
       const Trig t = trig_of(xa(k + 1, 4), xa(k + 1, 2));
       sx(k + 1, S_TR) = t.sn; sx(k + 1, S_TR + 1) = t.cs; sx(k + 1, S_TR + 2) = t.tn;
       for (int j = 0; j < 3; ++j) {
@@ -334,7 +334,7 @@ struct WarpSolver {
         const T c = h - P.r_sum;
         const T s = m_max(c, kp * m_max(T(1), P.r_sum));
         rc(k, R_S + j) = s;
-        rc(k, R_V + V_OB0 + j) = mu / s;
+        rc(k, R_V + V_OB0 + j) = mu * m_rcp(s);
       }
       for (int j = 0; j < 5; ++j) rc(k, R_DX + j) = T(0);
       rc(k, R_DU) = T(0); rc(k, R_DU + 1) = T(0);
@@ -425,7 +425,7 @@ struct WarpSolver {
           Ru1 += rc(k, R_V + V_A_LO) * isl;
           ru1 -= mu * isl;
         }
-        rc(k, R_RU) = Ru0; rc(k, R_RU + 1) = Ru1; rc(k, R_RU + 2) = ru0 * idt; rc(k, R_RU + 3) = ru1 * idt;
+        rc(k, R_RU) = Ru0 * (idt * idt); rc(k, R_RU + 1) = Ru1 * (idt * idt); rc(k, R_RU + 2) = ru0 * idt; rc(k, R_RU + 3) = ru1 * idt;
       }
     }
     w.sync();
@@ -443,7 +443,7 @@ struct WarpSolver {
   template <int HESS>
   MPC_HD bool backward_t() const {
     const int N = P.N;
-    const T dt = P.dt, dt2 = dt * dt;
+    const T dt = P.dt;
     T Pij = T(0);
     T lam[5] = {T(0), T(0), T(0), T(0), T(0)};
     const T ownf = (T)tb.own;
@@ -470,12 +470,13 @@ struct WarpSolver {
       const T q3 = w.shfl(Pij, tb.s1[3]), q4 = w.shfl(Pij, tb.s1[4]);
       fetch(nxt);   // next stage's record, off the dependent chain (at k = 0 a harmless read of the state records below)
       const T M = ownf * Pij + ((cur.c0 * q0 + cur.c1 * q1) + (cur.c2 * q2 + cur.c3 * q3) + cur.c4 * q4);
-      const T G00 = cur.Ru0 + dt2 * p22, G01 = dt2 * p23, G11 = cur.Ru1 + dt2 * p33;
+      // G / dt^2 (the stored control diagonal is pre-divided): J = -dt^2 G^-1 = -(G / dt^2)^-1 needs no dt^2 on the chain
+      const T G00 = cur.Ru0 + p22, G01 = p23, G11 = cur.Ru1 + p33;
       const T det = G00 * G11 - G01 * G01;
       if (HESS == HESS_EXACT) {
         if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) return false;      // uniform across lanes
       }
-      const T cdet = dt2 * m_rcp(det);
+      const T cdet = m_rcp(det);
       const T J00 = -cdet * G11, J01 = cdet * G01, J11 = -cdet * G00;
       // round 2
       const T m2j = w.shfl(M, tb.s_m2j), m3j = w.shfl(M, tb.s_m3j);
