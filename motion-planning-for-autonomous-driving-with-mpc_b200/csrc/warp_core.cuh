@@ -775,20 +775,24 @@ struct WarpSolver {
       if (k == 0) rts[10] = du1 * m_rcp(m_slack(u1 - st.a0_lo));          // stage-0 friction box, lower side
       }   // act
       if (sizeof(T) == 4) {
-        // float: branch-free per ratio -- a 4-term series below 0.02 (relative error < x^4/5 = 3e-8), otherwise one MUFU
-        // logarithm of u = 1 + x with the first-order correction (x - (u - 1)) / u for the rounding of u (relative error
-        // < 1e-5 there, on terms whose merit change is orders of magnitude above that).  12 log1pf calls were ~400
-        // instructions of the per-iteration instruction stream.
+        // float: ONE logarithm per stage -- the sum of the twelve log(1 + x_i) is the log of the product of the (1 + x_i)
+        // (one FFMA per row; 0.01^12 .. 100^12 stays inside the float range).  The product carries ~12 roundings (7e-7
+        // absolute in the log); these terms enter the merit times mu, next to cost terms whose own rounding is orders of
+        // magnitude larger, and the allowance below covers it.  log(prod): 4-term series in d = prod - 1 below 0.02
+        // (relative error < d^4/5 = 3e-8), else one MUFU logarithm.  (12 log1pf calls were ~400 instructions of the
+        // per-iteration instruction stream, 12 MUFU logarithms with rounding correction still ~180.)
+        T prod = T(1), xs = T(0);
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
           ok = ok && (rts[i] > T(-1));
           const T x = m_max(rts[i], T(-0.999999));
-          const T ser = x * (T(1) + x * (T(-0.5) + x * (T(1) / T(3) - T(0.25) * x)));
-          const T u = T(1) + x;
-          const T big = m_fastlog(u) + (x - (u - T(1))) * m_rcp(u);
-          const T l = (m_abs(x) < T(0.02)) ? ser : big;
-          lg += l; lga += m_abs(l);
+          prod += prod * x;
+          xs += m_abs(x);
         }
+        const T d = prod - T(1);
+        const T ser = d * (T(1) + d * (T(-0.5) + d * (T(1) / T(3) - T(0.25) * d)));
+        const T l = (m_abs(d) < T(0.02)) ? ser : m_fastlog(prod);
+        lg += l; lga += xs + T(2);
       } else {
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
