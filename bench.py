@@ -173,8 +173,11 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
-        # stdout carries exactly ONE line (the JSON): NCCL's debug output ("NCCL version ..." banner at NCCL_DEBUG=VERSION /
-        # WARN, which the box sets) goes to stderr instead
+        # stdout carries exactly ONE line (the JSON): NCCL's debug output (the "NCCL version ..." banner of NCCL_DEBUG=VERSION,
+        # which the box sets) goes to stderr instead.  NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION
+        # becomes WARN (same banner, plus warnings if any).
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local)
