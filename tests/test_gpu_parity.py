@@ -286,6 +286,14 @@ def test_float64_refinement_pass_converges_the_stalled_collision_avoidance_insta
         w = nlp.pack(Ur[b], Xr[b])
         r = ipm.solve(d, w)
         assert r["status"] == 1 and np.abs(r["w"] - w).max() < 1e-4          # was ~3e-3 before the refinement
+    # the same two-launch solve through the zero-copy host route: the refinement kernel reads the float32 pass's status and
+    # warm start from, and writes its result to, pinned HOST memory -- bit-identical to the device-buffer route
+    hx, hX, hU = optr.alloc_host_buffers(B)
+    hx[:] = xref
+    n0 = optr.handle.launch_count
+    Uh, Xh, sth, ith = optr.solve_batch_host(hx, out=(hX, hU))
+    assert optr.handle.launch_count - n0 == 2
+    assert np.array_equal(Uh, Ur) and np.array_equal(Xh, Xr) and np.array_equal(sth, str_) and np.array_equal(ith, itr)
 
 
 def test_long_horizon_and_small_horizon_edges():
