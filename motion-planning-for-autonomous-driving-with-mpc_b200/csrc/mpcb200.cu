@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(cons
   __shared__ __align__(8) uint64_t bar_w[WPC];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
-  const WLayout L(N);
+  const WLayout L(N, rec_stride_for(HM));
   const Smem<T, WPC> sm(smem_raw, N, L.words);
   const int nx = sm.nx, nu = sm.nu;
   const int base = blockIdx.x * WPC;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __
   unsigned char* const smem_raw = mpc_dyn_smem;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
-  const WLayout L(N);
+  const WLayout L(N, rec_stride_for(HM));
   const Smem<T, WPC> sm(smem_raw, N, L.words);
   const int nu = sm.nu;
   const int b = blockIdx.x * WPC + wid;
@@ -495,7 +495,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   h->launches = 0; h->slab = h->state = h->obs_shift = nullptr;
   h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
   h->sw_xref = nullptr; h->sw_B = 0;
-  const WLayout L(cfg->N);
+  const WLayout L(cfg->N, rec_stride_for(cfg->hessian == MPCB200_HESS_EXACT ? HESS_EXACT : HESS_GN));
   h->words = L.words;
   h->elem = cfg->precision == MPCB200_F64 ? 8 : 4;
   const size_t smem_max = prop.sharedMemPerBlockOptin;   // 227 KB on B200

@@ -42,13 +42,17 @@ enum : int {
   R_H = 31,     // 8  Hessian of the x_{k+1} terms: h00 h01 h04 h11 h14 h44 h22 h33
   R_GX = 39,    // 5  gradient of the x_{k+1} terms (barrier gradient at the current mu)
   R_RU = 44,    // 4  Ru0/dt^2 Ru1/dt^2 ru0/dt ru1/dt (control Hessian diagonal / gradient incl. barrier terms, pre-scaled for the sweep)
-  R_LC = 48,    // 5  multiplier-weighted gradient of the x_{k+1} terms (adjoint recursion, exact Hessian)
-  R_KK = 53,    // 12 gains times dt: dt*(K0[0..4] k0 K1[0..4] k1)
-  R_DX = 65,    // 5  step dx_{k+1}
-  R_DU = 70,    // 2  step du_k
-  R_FAR = 72,   // 1  obstacle rows of x_{k+1} screened out this iteration (1) or live (0)
-  REC_STRIDE = 73
+  R_KK = 48,    // 12 gains times dt: dt*(K0[0..4] k0 K1[0..4] k1)
+  R_DX = 60,    // 5  step dx_{k+1}
+  R_DU = 65,    // 2  step du_k
+  R_FAR = 67,   // 1  obstacle rows of x_{k+1} screened out this iteration (1) or live (0)
+  R_LC = 68,    // 5  multiplier-weighted gradient of the x_{k+1} terms (adjoint recursion: exact Hessian only, LAST so that
+                //    Gauss-Newton kernels use a shorter record)
+  REC_STRIDE = 73,      // record stride with the adjoint terms (exact Hessian, host emulator)
+  REC_STRIDE_GN = 69    // Gauss-Newton kernels: 68 words + 1 pad (odd strides keep lane = stage accesses bank-conflict free);
+                        // 480 B less per problem at N = 30 = the difference between 7 and 8 resident CTAs per SM
 };
+MPC_HD constexpr int rec_stride_for(int hessian_mode) { return hessian_mode == 0 /* HESS_GN */ ? REC_STRIDE_GN : REC_STRIDE; }
 // state record k = 0..N
 enum : int {
   S_XR = 0,     // 5 rho_k (reference row paired with stage k, frame shifted to the pinned position)
@@ -63,10 +67,10 @@ enum : int { H00 = 0, H01, H04, H11, H14, H44, H22, H33 };
 
 struct WLayout {
   int N, o_state, o_rec, words;
-  MPC_HD explicit WLayout(int N_) : N(N_) {
+  MPC_HD explicit WLayout(int N_, int rec_stride = REC_STRIDE) : N(N_) {
     o_state = 0;
     o_rec = ST_STRIDE * (N + 1);
-    words = (o_rec + REC_STRIDE * N + 3) & ~3;     // multiple of 4 words: 16-byte granularity for bulk copies
+    words = (o_rec + rec_stride * N + 3) & ~3;     // multiple of 4 words: 16-byte granularity for bulk copies
   }
 };
 
@@ -154,6 +158,7 @@ struct SlabRef {
 enum : int { HESS_RUNTIME = -1 };
 template <typename T, int HM = HESS_RUNTIME>
 struct WarpSolver {
+  static constexpr int RS = (HM == 0 /* HESS_GN */) ? REC_STRIDE_GN : REC_STRIDE;      // stage-record stride of this instantiation
   const ParamsT<T>& P;
   const WLayout L;
   const SlabRef<T> sl;   // this problem's slab
@@ -166,11 +171,11 @@ struct WarpSolver {
   const T irows;     // 1 / (number of inequality rows) = 1 / (10 N + 1)
 
   MPC_HD WarpSolver(const ParamsT<T>& P_, const SlabRef<T>& slab, const T* obs_, const WarpCtx& w_)
-      : P(P_), L(P_.N), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()), il_wb(T(1) / P_.l_wb), idt_(T(1) / P_.dt),
+      : P(P_), L(P_.N, RS), sl(slab), obs(obs_), w(w_), lane(w_.lane()), tb(w_.lane()), il_wb(T(1) / P_.l_wb), idt_(T(1) / P_.dt),
         irows(T(1) / T(10 * P_.N + 1)) {}
 
   MPC_HD T& sx(int k, int f) const { return sl[L.o_state + ST_STRIDE * k + f]; }
-  MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + REC_STRIDE * k + f]; }
+  MPC_HD T& rc(int k, int f) const { return sl[L.o_rec + RS * k + f]; }
   MPC_HD T xa(int k, int j) const { return sx(k, S_XT + j) + sx(k, S_XR + j); }
   struct RecRef {        // one stage record (serial sweeps: every lane reads the same record)
     const SlabRef<T>& s; int o;
@@ -410,7 +415,7 @@ struct WarpSolver {
       rc(k, R_H + H00) = hd[0]; rc(k, R_H + H01) = h01; rc(k, R_H + H04) = h04; rc(k, R_H + H11) = hd[1];
       rc(k, R_H + H14) = h14; rc(k, R_H + H44) = hd[4]; rc(k, R_H + H22) = hd[2]; rc(k, R_H + H33) = hd[3];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) { rc(k, R_GX + j) = g[j]; rc(k, R_LC + j) = lc[j]; }
+      for (int j = 0; j < 5; ++j) { rc(k, R_GX + j) = g[j]; if (HM != HESS_GN) rc(k, R_LC + j) = lc[j]; }
       // control terms
       {
         const T ilo = m_rcp(m_slack(u0 - P.dd_min)), ihi = m_rcp(m_slack(P.dd_max - u0));
@@ -449,7 +454,7 @@ struct WarpSolver {
     const T ownf = (T)tb.own;
     bool ok = true;
     // per-lane record pointers, bumped one record per stage (one IADD each instead of index arithmetic per load)
-    const int last = L.o_rec + REC_STRIDE * (N - 1);
+    const int last = L.o_rec + RS * (N - 1);
     const T* ph = &sl[last + tb.hidx];
     const T* pc0 = &sl[last + tb.c[0]]; const T* pc1 = &sl[last + tb.c[1]]; const T* pc2 = &sl[last + tb.c[2]];
     const T* pc3 = &sl[last + tb.c[3]]; const T* pc4 = &sl[last + tb.c[4]];
@@ -459,8 +464,8 @@ struct WarpSolver {
     auto fetch = [&](BwdCoef& q) {
       q.h = *ph; q.c0 = *pc0; q.c1 = *pc1; q.c2 = *pc2; q.c3 = *pc3; q.c4 = *pc4; q.e0 = *pe0; q.e1 = *pe1; q.e2 = *pe2;
       q.Ru0 = pr[0]; q.Ru1 = pr[1]; q.rp0 = pr[2]; q.rp1 = pr[3];
-      ph -= REC_STRIDE; pc0 -= REC_STRIDE; pc1 -= REC_STRIDE; pc2 -= REC_STRIDE; pc3 -= REC_STRIDE; pc4 -= REC_STRIDE;
-      pe0 -= REC_STRIDE; pe1 -= REC_STRIDE; pe2 -= REC_STRIDE; pr -= REC_STRIDE;
+      ph -= RS; pc0 -= RS; pc1 -= RS; pc2 -= RS; pc3 -= RS; pc4 -= RS;
+      pe0 -= RS; pe1 -= RS; pe2 -= RS; pr -= RS;
     };
     auto stage = [&](int k, const BwdCoef& cur, BwdCoef& nxt) -> bool {
       Pij += cur.h;                                   // x_{k+1} terms
@@ -486,11 +491,11 @@ struct WarpSolver {
       const T T0 = J00 * mm2 + J01 * mm3, T1 = J01 * mm2 + J11 * mm3;
       T Pn = (M + cur.e0 * r0) + (cur.e1 * r1 + cur.e2 * r2) + (m2i * T0 + m3i * T1);
       if (lane < 6) { pk[0] = T0; pk[6] = T1; }
-      pk -= REC_STRIDE;
+      pk -= RS;
       if (HESS == HESS_EXACT) {
         // adjoint multipliers lam_{k+1} (every lane keeps the 5-vector), then
         // + dt * sum_i lam_{k+1,i} * hess f_i(x_k) on the (delta, v, psi) block of P_k
-        const RecRef r{sl, L.o_rec + REC_STRIDE * k};
+        const RecRef r{sl, L.o_rec + RS * k};
 #pragma unroll
         for (int jj = 0; jj < 5; ++jj) lam[jj] += r[R_LC + jj];
         const T v = xa(k, 3);
@@ -546,7 +551,7 @@ struct WarpSolver {
     T* pd = &sl[L.o_rec + row];
     auto fetch = [&](FwdCoef& q) {
       q.f0 = *pf0; q.f1 = *pf1; q.f2 = *pf2; q.f3 = *pf3; q.f4 = *pf4; q.fc = *pfc; q.d = pd[R_D];
-      pf0 += REC_STRIDE; pf1 += REC_STRIDE; pf2 += REC_STRIDE; pf3 += REC_STRIDE; pf4 += REC_STRIDE; pfc += REC_STRIDE;
+      pf0 += RS; pf1 += RS; pf2 += RS; pf3 += RS; pf4 += RS; pfc += RS;
     };
     auto stage = [&](const FwdCoef& cur, FwdCoef& nxt) {
       const T acc = (cur.fc + cur.f0 * dx0) + (cur.f1 * dx1 + cur.f2 * dx2) + (cur.f3 * dx3 + cur.f4 * dx4);
@@ -555,7 +560,7 @@ struct WarpSolver {
       mine = nx;
       if (lane < 5) pd[R_DX] = nx;
       if (lane == 2 || lane == 3) pd[R_DU - 2] = acc * idt;
-      pd += REC_STRIDE;
+      pd += RS;
       fetch(nxt);   // at k = N-1 a harmless read just past the last record (still inside the CTA's shared memory)
     };
     FwdCoef ca, cb;
