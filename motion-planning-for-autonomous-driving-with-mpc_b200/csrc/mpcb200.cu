@@ -5,14 +5,15 @@
 //     (linearisation, residuals, merit, commit), entries of the 5x6 Riccati block [P | p] (KKT factor sweep) or state
 //     components (forward sweep) -- see warp_core.cuh;
 //   * the problem's whole KKT working set ("slab": iterate, reference, multipliers, slacks, stage KKT blocks, Riccati
-//     gains, step; 94N+21 words = 11.4 KB at N = 30 in fp32) lives in shared memory for the whole solve;
+//     gains, step; 90N+21 words = 10.9 KB at N = 30 in fp32, 94N+21 with the exact-Hessian adjoint words) lives in shared memory
+//     for the whole solve;
 //   * problem data moves HBM <-> shared memory with TMA bulk copies (cp.async.bulk + mbarrier): the CTA's float64
 //     xref/X/U rows are one contiguous chunk per array, and in the launch-per-iteration mode each warp's slab is one
 //     bulk load + one bulk store per launch;
 //   * all SQP iterations of a problem run inside one launch (problems are independent, so no grid-wide sync is ever
 //     needed) and a warp stops as soon as ITS problem has converged;
 //   * batch 1024 = 512 CTAs x 2 warps over 148 SMs (6-8 warps per SM, every SM busy); larger batches run in waves
-//     scheduled by the hardware (up to 7 CTAs of 28.6 KB resident per SM).
+//     scheduled by the hardware (up to 8 CTAs of 27.7 KB resident per SM in the Gauss-Newton kernels).
 // Tensor cores are not used: the factorisation works on 5x5/2x2 stage blocks along a length-N dependency chain.
 #include <cuda_runtime.h>
 #include <stdint.h>
