@@ -17,7 +17,7 @@
 //   * the forward sweep runs LANE = STATE COMPONENT (5 lanes + 5 broadcast shuffles per stage).
 //
 // The per-problem KKT slab (iterate, reference, multipliers, slacks, trig cache, stage KKT blocks, gains, step) is
-// 94N+21 words and lives in shared memory; stage records have an odd stride so LANE = STAGE accesses are
+// 90N+21 words (94N+21 with the exact-Hessian adjoint words) and lives in shared memory; stage records have an odd stride so LANE = STAGE accesses are
 // bank-conflict free and LANE = ENTRY accesses of one record are contiguous.
 //
 // New code: the reference contains no solver of its own (it calls casadi/IPOPT).  The same source compiles for the
