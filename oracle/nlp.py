@@ -9,6 +9,9 @@ holds no numeric assertion for the NLP optimum.  What IS pinned
 the plant model and Euler/RK4 steps against 254 recorded transitions (error 0.0), the circle geometry and the
 dynamics Jacobians against the CasADi-generated C in test/FORCESNLPsolver/FORCESNLPsolver_model.c (compiled into
 oracle/_ref by oracle/Makefile), the exact step-0 optimum a0* = -sqrt(11.5), and an independent scipy SLSQP solve.
+Statistically pinned in addition: every recorded step of the reference's own CasADi/IPOPT closed loops on ZAM_Over-1_1 (N = 10,
+applied control = optimum + N(0, sigma^2)) re-solved here leaves residuals with zero median and spread sigma
+(tests/test_oracle_golden.py::test_recorded_ipopt_controls_pin_the_oracle_optimum_statistically).
 
 Every function cites the reference lines it follows (paths relative to /root/reference/).
 
