@@ -1,14 +1,19 @@
 #!/usr/bin/env python3
 """bench.py -- MPC solves/sec on BASELINE.json's configs[1] (ZAM_Over-1_1 lane following, batch 1024 perturbed x0, N=30).
 
-One "step" = one pass of the hot path over one batch: `mpcb200_solve` (ONE fused kernel launch that runs every SQP
-iteration of its 1024 NLPs) on inputs already resident in HBM.  `value` = solves/s over all ranks (weak scaling: every
-rank owns its own copy of the seeded 1024-instance batch, no data-path collective).  `e2e` = the same metric through the public host-buffer call
-`B200Optimizer.solve_batch_host` (pinned host arrays, H2D + solve + D2H inside the timed region).
+One "step" = one pass of the hot path over one batch: `mpcb200_solve_cold` (ONE fused kernel launch that runs every SQP
+iteration of its 1024 NLPs, plus the float64 refinement launch that picks up whatever the float32 pass queued) on inputs
+already resident in HBM.  `value` = solves/s over all ranks, device-timed.  `e2e` = the same metric through the public
+host-buffer call `B200Optimizer.solve_batch_host` (pinned host arrays, H2D + solve + D2H inside the timed region).
+With N > 1 GPUs the line also carries `sharded`: rank 0 owns the N x 1024 global batch, NCCL scatters the parameter blocks,
+every rank solves its shard, NCCL gathers (U*, X*, status, iters) back -- all inside the timed region.
+`extra` holds the other single-GPU operating points (batch 8192, BASELINE configs[2] and configs[3]) so they are timed by
+whoever runs this file, and `parity` the instance-by-instance comparison with the float64 oracle.
 
   python bench.py [--gpus N --steps K --warmup W]          product arm (N>1 under torchrun, one rank per GPU)
-  python bench.py --impl reference [...]                   reference arm: the CPU restatement of the reference path (oracle/)
-                                                           on all host cores, bounded sample per step
+  python bench.py --impl reference [...]                   reference arm: the reference's CPU path on all host cores --
+                                                           casadi/IPOPT (oracle/casadi_ref.py) when importable, else the
+                                                           float64 restatement (oracle/ipm.py); the same 1024 instances per step
 """
 import argparse
 import json
@@ -27,8 +32,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENARIO, N_HORIZON, BATCH, SEED = "ZAM_Over-1_1_LF", 30, int(os.environ.get("MPCB200_BENCH_BATCH", "1024")), 20261017
+SCENARIO, N_HORIZON, BATCH, SEED = "ZAM_Over-1_1_LF", 30, 1024, 20261017
 METRIC = "MPC solves/sec (N=30, 5-state kinematic bicycle) at batch 1024"
+# the other operating points of BASELINE.json `configs` that fit one GPU: name, scenario, N, batch, seed
+EXTRA = {
+    "batch8192": ("ZAM_Over-1_1_LF", 30, 8192, SEED),
+    "config3_collision_avoidance": ("ZAM_Over-1_1_CA", 30, 4096, 20261018),
+    "config4_lanker_n50": ("USA_Lanker-2_18_T-1_LF", 50, 8192, 20261019),
+}
+SMSP_PER_SM = 4
 
 
 def bytes_iter(N):
@@ -36,7 +48,7 @@ def bytes_iter(N):
     return 4 * (219 * N + 65)
 
 
-# ------------------------------------------------------------------------------------------------ CPU (oracle) leg
+# ------------------------------------------------------------------------------------------------ CPU (oracle) legs
 def _oracle_one(args):
     name, N, xref, X, U = args
     import mpc_b200
@@ -47,15 +59,42 @@ def _oracle_one(args):
     return r["status"], r["iters"], r["w"]
 
 
+def _casadi_one(args):
+    name, N, xref, X, U = args
+    import mpc_b200
+    from oracle import casadi_ref
+    sc = mpc_b200.load_scenario(name)
+    w, ok = casadi_ref.solve_instance(sc, N, xref, X, U, rebuild=True)      # rebuilt per solve like the reference (Q10)
+    return (1 if ok else 0), 0, w
+
+
+def _warm_one(args):
+    """Local-optimum check of a candidate point (multi-modal NLPs): the float64 oracle warm-started AT the point must converge
+    and stay there.  Returns (oracle status, max |w_oracle - w|, obstacle clearance margin of the point)."""
+    name, N, xref, X, U = args
+    import mpc_b200
+    from oracle import nlp, ipm
+    sc = mpc_b200.load_scenario(name)
+    d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref, sc.static_obstacle)
+    w = nlp.pack(U, X)
+    r = ipm.solve(d, w)
+    clear = float(nlp.g_fun(d, w)[1 + 5 * (N + 1):].min() - d.r_sum)
+    return r["status"], float(np.abs(r["w"] - w).max()), clear
+
+
+def _pool(cores):
+    import multiprocessing as mp
+    return mp.get_context("fork").Pool(cores)
+
+
 def cpu_oracle_rate(n_sample, cores, pool=None):
     """Times the float64 oracle on the first n_sample instances of the workload over `cores` processes."""
-    import multiprocessing as mp
     import mpc_b200
     sc, x0, xref, X, U = mpc_b200.make_batch(SCENARIO, n_sample, N_HORIZON, SEED)
     jobs = [(SCENARIO, N_HORIZON, xref[b], X[b], U[b]) for b in range(n_sample)]
     own = pool is None
     if own:
-        pool = mp.get_context("fork").Pool(cores)
+        pool = _pool(cores)
         pool.map(_oracle_one, jobs[:cores])          # warm the workers (imports)
     t0 = time.perf_counter()
     res = pool.map(_oracle_one, jobs, chunksize=max(1, n_sample // (4 * cores)))
@@ -67,37 +106,42 @@ def cpu_oracle_rate(n_sample, cores, pool=None):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (restated: oracle/), all host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU path on all host cores, the SAME 1024 instances per step as the product arm.
+    casadi/IPOPT when importable (`kind: "ipopt"`, NLP rebuilt per solve like optimizer.py:605, quirk Q10), else the
+    float64 restatement (`kind: "port"`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_sample = max(cores, min(BATCH, 16 * cores))          # bounded sample per step (~0.5 s on all cores)
     import mpc_b200
-    sc, x0, xref, X, U = mpc_b200.make_batch(SCENARIO, n_sample, N_HORIZON, SEED)
-    jobs = [(SCENARIO, N_HORIZON, xref[b], X[b], U[b]) for b in range(n_sample)]
-    pool = mp.get_context("fork").Pool(cores)
-    pool.map(_oracle_one, jobs[:cores])
-    for _ in range(args.warmup):
-        pool.map(_oracle_one, jobs)
+    from oracle import casadi_ref
+    kind, fn, what = ("ipopt", _casadi_one, "casadi/IPOPT, verbatim reference NLP (oracle/casadi_ref.py), nlpsol rebuilt per solve") \
+        if casadi_ref.available() else ("port", _oracle_one, "float64 oracle (oracle/ipm.py)")
+    steps = args.steps if args.steps is not None else 5
+    warmup = args.warmup if args.warmup is not None else 1
+    sc, x0, xref, X, U = mpc_b200.make_batch(SCENARIO, BATCH, N_HORIZON, SEED)
+    jobs = [(SCENARIO, N_HORIZON, xref[b], X[b], U[b]) for b in range(BATCH)]
+    pool = _pool(cores)
+    pool.map(fn, jobs[:cores])
+    chunk = max(1, BATCH // (4 * cores))
+    for _ in range(warmup):
+        pool.map(fn, jobs, chunksize=chunk)
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        pool.map(_oracle_one, jobs)
+        res = pool.map(fn, jobs, chunksize=chunk)
         times.append(time.perf_counter() - t0)
     pool.close()
     total = sum(times)
-    value = n_sample * args.steps / total
+    value = BATCH * steps / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{SCENARIO} batch={BATCH} perturbed x0 N={N_HORIZON} (BASELINE configs[1])",
-                   "sample": f"first {n_sample} of the {BATCH} instances per step"},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} instances per step x {args.steps} steps, float64 oracle (oracle/ipm.py), "
-                                   f"multiprocessing.Pool({cores})"},
+        "config": {"workload": f"{SCENARIO} batch={BATCH} perturbed x0 (seed {SEED}) N={N_HORIZON} cold start (BASELINE configs[1])",
+                   "sample": f"all {BATCH} instances per step", "converged_last_step": sum(1 for r in res if r[0] == 1)},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind,
+                         "sample": f"{BATCH} instances per step x {steps} steps, {what}, multiprocessing.Pool({cores})"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -162,15 +206,118 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ product arm
+def _make_optimizer(name, N, B, device, args, solver_opts):
+    import mpc_b200
+    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
+    sc = mpc_b200.load_scenario(name)
+    return sc, B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=args.precision,
+                             hessian=args.hessian, max_batch=B, device=device, **solver_opts)
+
+
+class DeviceWorkload:
+    """One seeded synthetic batch resident in HBM + the timed step (cold start: X / U are outputs only)."""
+
+    def __init__(self, name, N, B, seed, dev, args, solver_opts, torch):
+        import mpc_b200
+        self.torch, self.N, self.B, self.name = torch, N, B, name
+        self.sc, self.x0, self.xref, X0, U0 = mpc_b200.make_batch(name, B, N, seed)
+        assert np.array_equal(X0, np.repeat(self.xref[:, :1], N + 1, axis=1)) and not U0.any()      # the workload IS the cold start
+        _, self.opt = _make_optimizer(name, N, B, dev.index, args, solver_opts)
+        f64 = torch.float64
+        self.d_xref = torch.as_tensor(self.xref, device=dev)
+        self.d_X = torch.empty(B, N + 1, 5, dtype=f64, device=dev)
+        self.d_U = torch.empty(B, N, 2, dtype=f64, device=dev)
+        self.d_status = torch.empty(B, dtype=torch.int32, device=dev)
+        self.d_iters = torch.empty(B, dtype=torch.int32, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
+
+    def step(self):
+        h = self.opt.handle
+        h.check(h.lib.mpcb200_solve_cold(h.h, self.d_xref.data_ptr(), self.d_X.data_ptr(), self.d_U.data_ptr(), self.d_status.data_ptr(),
+                                         self.d_iters.data_ptr(), self.B, self.stream.cuda_stream))
+
+    def timed(self, steps, warmup, flush):
+        """CUDA events on the launching stream around each step, L2 flushed between steps.  Returns ms per step (array)."""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            flush.fill_(1.0); self.step()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s_, e_ in ev:
+            flush.fill_(1.0)                 # evict L2 between timed iterations
+            s_.record(self.stream); self.step(); e_.record(self.stream)
+        torch.cuda.synchronize()
+        return np.array([s_.elapsed_time(e_) for s_, e_ in ev])
+
+    def results(self):
+        return self.d_X.cpu().numpy(), self.d_U.cpu().numpy(), self.d_status.cpu().numpy(), self.d_iters.cpu().numpy()
+
+
+def _extra_point(key, dev, args, solver_opts, torch, flush, cores, do_parity):
+    """One of the other single-GPU operating points: device-timed throughput (+ parity against the oracle on all host cores)."""
+    name, N, B, seed = EXTRA[key]
+    wl = DeviceWorkload(name, N, B, seed, dev, args, dict(max_iter=300, **solver_opts), torch)
+    steps = 20
+    ms = wl.timed(steps, 3, flush)
+    X, U, st, it = wl.results()
+    out = {"workload": f"{name} batch={B} N={N} seed {seed} cold start", "solves_per_s": B * steps / (ms.sum() * 1e-3),
+           "ms_per_step": float(ms.mean()), "steps": steps, "converged": f"{int((st == 1).sum())}/{B}",
+           "status_counts": {str(int(k)): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
+           "mean_sqp_iters": float(it.mean()), "max_sqp_iters": int(it.max()),
+           "roofline_frac_model": float(it.sum()) * bytes_iter(N) / (ms.mean() * 1e-3) / 1e9 / _peak()[0]}
+    if do_parity and key == "config3_collision_avoidance":
+        # multi-modal from a cold start (several local minima around the obstacle): parity = every GPU point is within the stated
+        # tolerance of a local optimum of the reference NLP -- the float64 oracle warm-started AT the GPU point converges and stays
+        with _pool(cores) as pool:
+            res = pool.map(_warm_one, [(name, N, wl.xref[b], X[b], U[b]) for b in range(B)], chunksize=8)
+        sto = np.array([r[0] for r in res]); dw = np.array([r[1] for r in res]); clr = np.array([r[2] for r in res])
+        out["parity"] = {"checked": int((sto == 1).sum()), "of": B, "max_abs_dw": float(dw[sto == 1].max()), "tolerance": 1e-3,
+                         "n_above_tolerance": int((dw[sto == 1] > 1e-3).sum()), "min_clearance_margin_m": float(clr.min()),
+                         "against": "float64 oracle warm-started at the GPU point (local optimum of the restated reference NLP), every instance"}
+    if do_parity and key == "config4_lanker_n50":
+        n_chk = 1024
+        idx = np.linspace(0, B - 1, n_chk).astype(int)
+        X0 = np.repeat(wl.xref[:, :1], N + 1, axis=1)
+        with _pool(cores) as pool:
+            res = pool.map(_oracle_one, [(name, N, wl.xref[b], X0[b], np.zeros((N, 2))) for b in idx], chunksize=4)
+        from oracle import nlp as _nlp
+        dU = dX = 0.0
+        n_cmp = 0
+        for b, (st_o, _, w_o) in zip(idx, res):
+            if st_o == 1 and st[b] == 1:
+                Uo, Xo = _nlp.split(w_o, N)
+                dU = max(dU, float(np.abs(Uo - U[b]).max())); dX = max(dX, float(np.abs(Xo - X[b]).max()))
+                n_cmp += 1
+        out["parity"] = {"checked": n_cmp, "of": B, "sample": f"{n_chk} evenly spaced instances", "max_abs_dU": dU, "max_abs_dX": dX, "tolerance": 1e-3,
+                         "against": "float64 oracle (restated reference NLP)"}
+    return out
+
+
+_PEAK = None
+
+
+def _peak():
+    global _PEAK
+    if _PEAK is None:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        _PEAK = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+    return _PEAK
+
+
 def run_product(args):
     import torch
     import mpc_b200
-    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    steps = args.steps if args.steps is not None else 200
+    warmup = max(args.warmup if args.warmup is not None else 5, 3)
     dist = None
     if world > 1:
         # stdout carries exactly ONE line (the JSON): NCCL's debug output (the "NCCL version ..." banner of NCCL_DEBUG=VERSION,
@@ -186,39 +333,21 @@ def run_product(args):
         torch.cuda.set_device(0)
         local = 0
     dev = torch.device("cuda", local)
-    N, B = N_HORIZON, BATCH
-    # weak scaling: every rank owns its own copy of the seeded config-2 batch (seed 20261017), so the per-GPU work
-    # is EXACTLY the same at every N (with per-rank seeds the slowest draw -- the instance with the most SQP iterations --
-    # would set the max-over-ranks time and read as a scaling loss); no data-path collective
-    sc, x0, xref, X0, U0 = mpc_b200.make_batch(SCENARIO, B, N, SEED)
+    N, B = N_HORIZON, args.batch
     solver_opts = {}
     for kv in args.opt:                                   # tuning knob: fields of mpcb200_config, e.g. --opt mu_min=1e-6
         k, v = kv.split("=")
-        solver_opts[k] = int(v) if k in ("max_iter", "ls_max", "acc_iters", "stall_iters", "refine_f64", "init_rollout") else float(v)
-    opt = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=args.precision,
-                        hessian=args.hessian, max_batch=B, device=local, **solver_opts)
+        solver_opts[k] = float(v)
     f64 = torch.float64
-    d_xref = torch.as_tensor(xref, device=dev)
-    assert np.array_equal(X0, np.repeat(xref[:, :1], N + 1, axis=1)) and not U0.any()      # the workload IS the cold start
-    d_X = torch.empty(B, N + 1, 5, dtype=f64, device=dev); d_U = torch.empty(B, N, 2, dtype=f64, device=dev)
-    d_status = torch.empty(B, dtype=torch.int32, device=dev)
-    d_iters = torch.empty(B, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
-    h, stream = opt.handle, torch.cuda.current_stream(dev)
-
-    def step():
-        # cold start = the reference's step-0 initial guess (X_0 tiled, zero controls): X / U are outputs only
-        h.check(h.lib.mpcb200_solve_cold(h.h, d_xref.data_ptr(), d_X.data_ptr(), d_U.data_ptr(), d_status.data_ptr(),
-                                         d_iters.data_ptr(), B, stream.cuda_stream))
-
-    def reset():
-        flush.fill_(1.0)                     # evict L2 between timed iterations
-
-    for _ in range(max(args.warmup, 3)):
-        reset(); step()
+    # weak scaling: every rank's shard is the seeded config-2 batch (seed 20261017), so the per-GPU work is EXACTLY
+    # the same at every N (with per-rank seeds the slowest draw -- the instance with the most SQP iterations -- would set the
+    # max-over-ranks time and read as a scaling loss)
+    wl = DeviceWorkload(SCENARIO, N, B, SEED, dev, args, solver_opts, torch)
+    opt, h = wl.opt, wl.opt.handle
+    for _ in range(warmup):
+        flush.fill_(1.0); wl.step()
     torch.cuda.synchronize(dev)
-    status = d_status.cpu().numpy(); iters = d_iters.cpu().numpy()
-    n_ok = int((status == 1).sum())
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -226,10 +355,11 @@ def run_product(args):
         dist.barrier()
     torch.cuda.synchronize(dev)
     n0 = h.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ms = wl.timed(steps, 0, flush) if False else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for s_, e_ in ev:
-        reset()
-        s_.record(stream); step(); e_.record(stream)
+        flush.fill_(1.0)
+        s_.record(wl.stream); wl.step(); e_.record(wl.stream)
     torch.cuda.synchronize(dev)
     if dist:
         dist.barrier()
@@ -240,8 +370,11 @@ def run_product(args):
         t = torch.tensor([total_ms], device=dev, dtype=f64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+    Xg, Ug, status, iters = wl.results()
+    n_ok = int((status == 1).sum())
+
     # ---- end-to-end through the public host-buffer API (pinned host memory, H2D + solve + D2H per step)
-    hx = torch.as_tensor(xref).pin_memory()
+    hx = torch.as_tensor(wl.xref).pin_memory()
     hX = torch.empty(B, N + 1, 5, dtype=f64).pin_memory(); hU = torch.empty(B, N, 2, dtype=f64).pin_memory()   # pinned result buffers
     for _ in range(3):
         opt.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
@@ -250,50 +383,92 @@ def run_product(args):
     torch.cuda.synchronize(dev)
     n1 = h.launch_count
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         Ue, Xe, ste, ite = opt.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     assert (ste == 1).all() and float(Ue[0, 0, 1]) == float(Ue[0, 0, 1])               # the result was read back
     launches += h.launch_count - n1
+    e2e_per_rank = None
     if dist:
-        t = torch.tensor([e2e_s], device=dev, dtype=f64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        tl = [torch.zeros(1, device=dev, dtype=f64) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([e2e_s], device=dev, dtype=f64))
+        e2e_per_rank = [float(x.item()) for x in tl]
+        e2e_s = max(e2e_per_rank)
         dist.barrier()
+    # the same call with ordinary (pageable) numpy arrays -- what a caller that does not pin its buffers gets (staged route)
+    xp = np.array(wl.xref)
+    for _ in range(2):
+        opt.solve_batch_host(xp)
+    n_pg = max(5, steps // 10)
+    t0 = time.perf_counter()
+    for _ in range(n_pg):
+        opt.solve_batch_host(xp)
+    pageable_s = (time.perf_counter() - t0) / n_pg
+
+    # ---- sharded mode (N > 1): rank 0 owns the global batch; NCCL scatter -> solve -> NCCL gather, all timed
+    sharded = None
+    if dist:
+        from mpc_b200 import sharding
+        Bg = world * B
+        g_xref = torch.as_tensor(np.tile(wl.xref, (world, 1, 1)), device=dev) if rank == 0 else None
+        sh_steps = min(steps, 50)
+        ev2 = []
+        for i in range(3 + sh_steps):
+            flush.fill_(1.0)
+            dist.barrier()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(wl.stream)
+            res = sharding.solve_sharded_nccl(opt, g_xref, Bg, N, src=0)
+            e_.record(wl.stream)
+            if i >= 3:
+                ev2.append((s_, e_))
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([sum(s_.elapsed_time(e_) for s_, e_ in ev2)], device=dev, dtype=f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sh_ms = float(t.item()) / sh_steps
+        ok_all = None
+        if rank == 0:
+            Ush, Xsh, stsh, itsh = res
+            ok_all = bool((stsh == 1).all().item()) and bool(torch.equal(Ush[:B], wl.d_U)) and bool(torch.equal(Ush[-B:], wl.d_U))
+        nxb, nub = 5 * (N + 1) * 8, 2 * N * 8
+        sharded = {"value": Bg * 1e3 / sh_ms, "unit": "solves/s", "ms_per_step": sh_ms, "global_batch": Bg, "steps": sh_steps,
+                   "collective": "NCCL scatter of xref shards from rank 0, NCCL gather of (U*, X*, status, iters) to rank 0 (torch.distributed)",
+                   "scatter_bytes_per_step": (world - 1) * B * nxb, "gather_bytes_per_step": (world - 1) * B * (nxb + nub + 8),
+                   "collective_us_per_step": 1e3 * sh_ms - 1e3 * total_ms / steps,
+                   "gathered_equals_single_gpu_solve_bitwise": ok_all,
+                   "timing": "CUDA events on the launching stream, barrier before each step, max over ranks"}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant (only) kernel: algorithmic bytes of one launch / its mean duration
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs, burst)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    # ---- model roofline of the dominant (only) kernel + what actually binds it
+    peak, peak_src = _peak()
     alg_bytes = float(iters.sum()) * bytes_iter(N)
-    launch_ms = total_ms / args.steps
+    launch_ms = total_ms / steps
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = warp_inst = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
         traffic = prof.get("dram_bytes_per_launch")
+        warp_inst = prof.get("warp_instructions_per_launch")
     except Exception:
         pass
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only at N=1
-    cpu = None
-    parity = None
+    props = torch.cuda.get_device_properties(dev)
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_frac = None
+    if warp_inst:
+        issue_frac = warp_inst / (props.multi_processor_count * SMSP_PER_SM * sm_hz * 1e6 * launch_ms * 1e-3)
+    # ---- CPU baseline (oracle port) + parity on all host cores, rank 0 only at N=1
+    cpu = parity = extra = None
+    cores = os.cpu_count() or 1
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        n_sample = BATCH                                   # the whole workload: ~25 ms per solve per core, 10-40 core-seconds
-        rate, dt, ok, ores = cpu_oracle_rate(n_sample, cores)
+        rate, dt, ok, ores = cpu_oracle_rate(B, cores)
         cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": f"first {n_sample} of the {BATCH} instances, float64 oracle (oracle/ipm.py), Pool({cores}), {dt:.1f} s, {ok} converged"}
+               "sample": f"all {B} instances of the timed batch, float64 oracle (oracle/ipm.py), Pool({cores}), {dt:.1f} s, {ok} converged"}
         # the oracle solutions of that leg double as the checker of the timed GPU results (same instances, same cold start)
         from oracle import nlp as _nlp
-        Xg, Ug = d_X.cpu().numpy(), d_U.cpu().numpy()
         dU = dX = 0.0
         n_cmp = 0
         for b, (st_o, _, w_o) in enumerate(ores):
@@ -303,28 +478,46 @@ def run_product(args):
                 n_cmp += 1
         parity = {"checked": n_cmp, "of": B, "max_abs_dU": dU, "max_abs_dX": dX, "tolerance": 1e-3,
                   "against": "float64 oracle (restated reference NLP), every instance of the timed batch"}
+    if world == 1 and not args.no_extra:
+        extra = {}
+        del wl
+        for key in EXTRA:
+            extra[key] = _extra_point(key, dev, args, solver_opts, torch, flush, cores, do_parity=not args.no_cpu_baseline)
     nx, nu = 5 * (N + 1), 2 * N
     line = {
-        "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "solves/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "metric": METRIC, "value": world * B * steps / (total_ms * 1e-3), "unit": "solves/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
         "p50_ms_per_step": float(np.median(ms)), "p50_ms_per_solve": float(np.median(ms)) / B,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"{SCENARIO} batch={B} perturbed x0 (seed {SEED}) N={N} cold start (BASELINE configs[1]); every rank solves its own copy",
-                   "parallelism": f"batch-shard x{world} (independent NLPs, no data-path collective)",
+        "config": {"workload": f"{SCENARIO} batch={B} perturbed x0 (seed {SEED}) N={N} cold start (BASELINE configs[1]); every rank's shard is this batch",
+                   "parallelism": f"batch-shard x{world} (independent NLPs, no data-path collective; `sharded` adds the NCCL scatter / gather)",
                    "l2": "256 MB flush write between timed iterations", "hessian": args.hessian, **({"solver_opts": solver_opts} if solver_opts else {}),
-                   "converged": f"{n_ok}/{B}", "mean_sqp_iters": float(iters.mean()), "max_sqp_iters": int(iters.max())},
-        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": B * nx * 8,
-                "d2h_bytes_per_step": B * (nx + nu) * 8 + B * 8, "ms_per_step": 1e3 * e2e_s / args.steps},
+                   "converged": f"{n_ok}/{B}", "mean_sqp_iters": float(iters.mean()), "max_sqp_iters": int(iters.max()),
+                   "launches_per_step": launches / (2.0 * steps)},
+        "e2e": {"value": world * B * steps / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": B * nx * 8,
+                "d2h_bytes_per_step": B * (nx + nu) * 8 + B * 8, "ms_per_step": 1e3 * e2e_s / steps,
+                "buffers": "caller-pinned host arrays (zero-copy route: the kernel reads / writes host memory over PCIe)",
+                **({"per_rank_ms_per_step": [1e3 * x / steps for x in e2e_per_rank]} if e2e_per_rank else {}),
+                "pageable_ms_per_step": 1e3 * pageable_s,
+                "pageable_note": "same call with ordinary numpy arrays: staged H2D / solve / D2H pipeline inside the library"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "mpc_warp_solve_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "algorithmic bytes = sum over problems of SQP iterations x 4(219N+65) B (KKT slab staged once per iteration); "
-                             "the fused kernel keeps the slab in shared memory, so real DRAM traffic is far below this"},
+                     "issue_frac": issue_frac,
+                     "note": "MODEL figure: algorithmic bytes = sum over problems of SQP iterations x 4(219N+65) B (SURVEY 8d: the KKT slab staged "
+                             "once per iteration) / the launch time.  The fused kernel keeps the slab in shared memory: measured DRAM traffic "
+                             "(`traffic`, ncu) is ~100x smaller, HBM does not bind this kernel.  What binds it is instruction issue on a dependent "
+                             "chain: `issue_frac` = warp instructions per launch (ncu, profiles/latest_traffic.json) / (SMs x 4 sub-partitions x "
+                             "SM clock x launch time)"},
         "cpu_baseline": cpu,
         "parity": parity,
         "clocks": clocks,
     }
+    if sharded:
+        line["sharded"] = sharded
+    if extra:
+        line["extra"] = extra
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
@@ -333,12 +526,14 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 product arm, 5 reference arm)")
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--hessian", default="gn", choices=["exact", "gn"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="experiments only: batch of the headline workload (the metric is quoted at 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other single-GPU operating points")
     ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments; default: none)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCB200_ABI_VERSION 3
+#define MPCB200_ABI_VERSION 4
 
 enum { MPCB200_F32 = 0, MPCB200_F64 = 1 };
 enum { MPCB200_HESS_GAUSS_NEWTON = 0, MPCB200_HESS_EXACT = 1 };
@@ -73,6 +73,14 @@ typedef struct mpcb200_config {
   int32_t stall_iters;             /* status 3 after this many iterations at mu_min without halving the step (noise floor) */
   int32_t refine_f64;              /* precision F32 only: re-solve instances that did not reach status 1 in float64 arithmetic (second launch) */
   int32_t init_rollout;            /* 1: initial states = Euler rollout of the initial controls from X_0 (X warm start ignored) */
+  /* ---- ABI 4 */
+  double mu_warm;                  /* dual warm start: barrier parameter a warm-started solve restarts at (instead of mu0) */
+  double warm_push;                /* dual warm start: relative interior push of the warm primal point (instead of bound_push) */
+  double kappa_warm;               /* dual warm start: carried multipliers are kept within [mu_warm/(kappa s), kappa mu_warm/s] */
+  int32_t warm_duals;              /* mpcb200_closed_loop: 1 = carry slacks / multipliers across MPC steps (shifted one stage), 0 = IPOPT-like restart every step */
+  int32_t warps_per_cta;           /* problems (= warps) per CTA: 0 = library default, else 1 | 2 | 4 */
+  int32_t host_route;              /* mpcb200_solve_host: 0 = zero-copy when every buffer is pinned, else staged; 1 = always staged */
+  int32_t host_chunks;             /* staged host route: chunks of the copy / solve / copy pipeline, 0 = by batch size */
 } mpcb200_config;
 
 typedef struct mpcb200_handle mpcb200_handle;

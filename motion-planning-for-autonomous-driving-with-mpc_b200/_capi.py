@@ -6,14 +6,16 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpcb200.so")
+# MPCB200_LIB: development aid -- load another BUILD of the same library (e.g. a variant compiled with different flags for an
+# A/B measurement).  There is still no fallback: whatever path is named must exist and export the ABI.
+LIB_PATH = os.environ.get("MPCB200_LIB") or os.path.join(_HERE, "csrc", "libmpcb200.so")
 
 F32, F64 = 0, 1
 HESS_GAUSS_NEWTON, HESS_EXACT = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # status codes (mirror test/FORCESNLPsolver/include/FORCESNLPsolver.h:70-106)
-ST_OPTIMAL, ST_MAXIT, ST_NAN, ST_NOPROGRESS, ST_INFEASIBLE_X0 = 1, 0, -6, -7, -8
+ST_OPTIMAL, ST_MAXIT, ST_STALLED, ST_NAN, ST_NOPROGRESS, ST_INFEASIBLE_X0 = 1, 0, 3, -6, -7, -8
 
 
 class Config(C.Structure):
@@ -27,7 +29,9 @@ class Config(C.Structure):
                  ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_factor", C.c_double), ("tol_step", C.c_double),
                  ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double), ("mu_min_alpha", C.c_double), ("mu_up_alpha", C.c_double), ("mu_up_factor", C.c_double), ("mu_max", C.c_double), ("mu_factor_full", C.c_double),
                  ("kappa_sigma", C.c_double), ("screen_inv_curv", C.c_double), ("trust_step", C.c_double), ("acc_factor", C.c_double),
-                 ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32)])
+                 ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32),
+                 ("mu_warm", C.c_double), ("warm_push", C.c_double), ("kappa_warm", C.c_double),
+                 ("warm_duals", C.c_int32), ("warps_per_cta", C.c_int32), ("host_route", C.c_int32), ("host_chunks", C.c_int32)])
 
 
 EXPORTS = {
@@ -80,6 +84,20 @@ def load():
 def default_config(N, precision=F32):
     cfg = Config()
     load().mpcb200_default_config(C.byref(cfg), N, precision)
+    return cfg
+
+
+_INT_FIELDS = {n for n, t in Config._fields_ if t is C.c_int32}
+_SCALAR_FIELDS = {n for n, t in Config._fields_ if t in (C.c_int32, C.c_double)}
+
+
+def set_options(cfg, opts):
+    """Apply solver options (fields of mpcb200_config) by name.  A name that is not a scalar field of the struct is an error:
+    `setattr` on a ctypes.Structure would otherwise create a plain Python attribute and the option would be silently ignored."""
+    for k, v in opts.items():
+        if k not in _SCALAR_FIELDS:
+            raise Mpcb200Error(f"unknown solver option {k!r}; mpcb200_config has: {sorted(_SCALAR_FIELDS)}")
+        setattr(cfg, k, int(v) if k in _INT_FIELDS else float(v))
     return cfg
 
 

@@ -25,6 +25,7 @@
 
 #include "config_params.h"
 #include "warp_core.cuh"
+#include "loop_core.cuh"
 
 using namespace mpcb200;
 
@@ -61,6 +62,14 @@ __device__ __forceinline__ void tma_store_commit_wait() {
 // ===================================================================================================== kernel args
 enum : int { MODE_ONESHOT = 0, MODE_BEGIN = 1, MODE_ITER = 2, MODE_END = 3 };
 
+// device-side work counters of a handle (self-resetting: the last warp to leave a launch that used them zeroes them)
+struct WorkCtr {
+  int next;       // next unclaimed work item beyond the statically assigned first wave
+  int done;       // warps that have left the launch
+  int q_count;    // refinement queue: problems the float32 pass did not bring to status 1
+  int q_pad;
+};
+
 template <typename T>
 struct SolveArgs {
   ParamsT<T> P;
@@ -75,14 +84,20 @@ struct SolveArgs {
   T* slab;              // global image of the slabs [B][words] (stepwise mode)
   ProbState<T>* state;  // [B] (stepwise mode)
   T* obs_shift;         // [B][6] shifted obstacle centres (stepwise mode)
+  WorkCtr* ctr;         // work counters (dynamic scheduling beyond the first wave, refinement queue)
+  int* q_list;          // [max_batch] refinement queue: written by the float32 pass, consumed by the float64 pass
   int B;
   int mode;
   int n_iter;
   int cold;             // 1: X / U are outputs only (cold start: X_0 tiled, zero controls)
-  int refine;           // 1: second pass -- only instances whose status is not 1 are solved (warm start = their X / U)
+  int refine;           // 1: float64 refinement pass -- the work list is q_list[0 .. q_count), warm start = the float32 X / U
+  int dynamic;          // 1: B exceeds the launch's warps: warps claim further problems from ctr->next
 };
 
-// shared-memory carve-up of one CTA: [WPC slabs of T][float64 staging: xref | X | U for WPC problems]
+// shared-memory carve-up of one CTA: [WPC slabs of T][WPC float64 xref staging blocks of (5(N+1) + 1 rounded up to even) doubles]
+// The staging block has one spare double in front: a row whose global address is 8 (mod 16) is placed 8 bytes in, so that the
+// 16-byte-aligned interior the TMA bulk copy moves is 16-byte aligned on both sides.
+MPC_HD int stg_doubles(int N) { return (5 * (N + 1) + 2) & ~1; }
 template <typename T, int WPC>
 struct Smem {
   int nx, nu;
@@ -90,236 +105,178 @@ struct Smem {
   unsigned char* raw;
   __device__ Smem(unsigned char* raw_, int N, int words) : nx(5 * (N + 1)), nu(2 * N), slab_bytes((size_t)words * sizeof(T)), raw(raw_) {}
   __device__ T* slab(int w) const { return reinterpret_cast<T*>(raw + (size_t)w * slab_bytes); }
-  __device__ double* xref(int w = 0) const { return reinterpret_cast<double*>(raw + (size_t)WPC * slab_bytes) + (size_t)w * nx; }
-  __device__ double* X(int w = 0) const { return xref(0) + (size_t)WPC * nx + (size_t)w * nx; }
-  __device__ double* U(int w = 0) const { return xref(0) + (size_t)2 * WPC * nx + (size_t)w * nu; }
+  __device__ double* xstg(int w) const { return reinterpret_cast<double*>(raw + (size_t)WPC * slab_bytes) + (size_t)w * stg_doubles(nu / 2); }
 };
 static size_t smem_bytes_for(int N, int words, size_t elem, int wpc) {
-  return (size_t)wpc * ((size_t)words * elem + (size_t)(12 * N + 10) * sizeof(double));
+  return (size_t)wpc * ((size_t)words * elem + (size_t)stg_doubles(N) * sizeof(double));
 }
 
-// CTA-cooperative tile copies HBM <-> float64 staging.  A full tile whose byte count is a multiple of 16 moves as TMA
-// bulk copies (one elected thread, completion on an mbarrier / bulk group); a ragged last tile uses plain loops.
-template <int WPC>
-__device__ __forceinline__ bool tile_is_bulk(int nvalid, int per_problem) {
-  return nvalid == WPC && ((WPC * per_problem * (int)sizeof(double)) % 16) == 0;
+// One problem's xref block HBM (or pinned host memory) -> the warp's staging: the 16-byte-aligned interior by ONE TMA bulk copy
+// issued by lane 0 (completion on the warp's mbarrier), the 8-byte head / tail words a misaligned row leaves by plain loads.
+// Returns the staging address of the row.  Works for every 8-byte-aligned address (odd problem index at even N, sliced tensors).
+__device__ __forceinline__ const double* fetch_xref(const double* g, double* stg, int nx, uint64_t* bar, uint32_t& phase, int lane) {
+  const uint32_t head = (uint32_t)((uintptr_t)g & 8u);                 // 0 or 8 bytes in front of the aligned interior
+  const uint32_t bytes = (uint32_t)nx * 8u;
+  const uint32_t interior = (bytes - head) & ~15u;
+  double* row = stg + (head >> 3);
+  // the staging was last read through the generic proxy (previous problem): order those reads before the async-proxy write
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    mbar_expect_tx(bar, interior);
+    tma_load_1d(reinterpret_cast<unsigned char*>(row) + head, reinterpret_cast<const unsigned char*>(g) + head, interior, bar);
+  }
+  if (lane == 1 && head) row[0] = g[0];
+  if (lane == 2 && head + interior < bytes) row[nx - 1] = g[nx - 1];
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+  __syncwarp();
+  return row;
 }
+
+// resident warps per SM the float32 kernels are compiled for: 16 = 4 per sub-partition = 128 registers per thread at most (the
+// kernel needs ~120); 18-20 would need <= 96 registers (a sub-partition then holds 5 warps) and spills
+#ifndef MPC_WARPS_PER_SM
+#define MPC_WARPS_PER_SM 16
+#endif
+template <typename T, int WPC> struct MinBlocks { static constexpr int v = (sizeof(T) == 4 ? MPC_WARPS_PER_SM : 8) / WPC; };
 
 // ===================================================================================================== solve kernel
-// One warp per ego instance; WPC warps (problems) per CTA.  All SQP iterations of a problem run inside the launch
-// (MODE_ONESHOT), or `n_iter` of them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
+// One warp per ego instance, PERSISTENT: a warp solves problem (global warp index), then claims further problems from a
+// device counter until the batch is empty -- problems need 4 ... 60 SQP iterations, so static pairing would idle a finished
+// warp until its CTA partner is done.  All SQP iterations of a problem run inside the launch (MODE_ONESHOT), or `n_iter` of
+// them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
 template <typename T, int WPC, int HM>
-__global__ void __launch_bounds__(32 * WPC, 16 / WPC) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
+__global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
-  __shared__ __align__(8) uint64_t bar_io;
-  __shared__ __align__(8) uint64_t bar_w[WPC];
+  __shared__ __align__(8) uint64_t bar_x[WPC];     // xref staging
+  __shared__ __align__(8) uint64_t bar_w[WPC];     // slab image (stepwise modes)
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
   const WLayout L(N, rec_stride_for(HM));
   const Smem<T, WPC> sm(smem_raw, N, L.words);
   const int nx = sm.nx, nu = sm.nu;
-  const int base = blockIdx.x * WPC;
-  const int nvalid = min(WPC, a.B - base);
-  const bool valid = wid < nvalid;
-  const int b = base + (valid ? wid : 0);
+  const int total_warps = gridDim.x * WPC;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar_io, 1);
 #pragma unroll
-    for (int i = 0; i < WPC; ++i) mbar_init(&bar_w[i], 1);
+    for (int i = 0; i < WPC; ++i) { mbar_init(&bar_x[i], 1); mbar_init(&bar_w[i], 1); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
+  __syncthreads();                                  // the only CTA-wide barrier: from here on the warps are independent
 
   const WarpCtx w;
   T obs[6];
   WarpSolver<T, HM> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
-  ProbState<T> st;
   const bool need_xref = (a.mode != MODE_ITER);
   const bool need_init = (a.mode == MODE_ONESHOT || a.mode == MODE_BEGIN);
   const bool need_warm = need_init && !a.cold;
+  const int nwork = a.refine ? a.ctr->q_count : a.B;
+  uint32_t ph_x = 0, ph_w = 0;
 
-  // ---- problem data in: xref (+ warm start) of the CTA's tile, HBM -> staging
-  if (need_xref) {
-    if (tile_is_bulk<WPC>(nvalid, nx) && tile_is_bulk<WPC>(nvalid, nu)) {
-      if (threadIdx.x == 0) {
-        const uint32_t bx = (uint32_t)(WPC * nx * sizeof(double)), bu = (uint32_t)(WPC * nu * sizeof(double));
-        mbar_expect_tx(&bar_io, need_warm ? (2 * bx + bu) : bx);
-        tma_load_1d(sm.xref(), a.xref + (size_t)base * nx, bx, &bar_io);
-        if (need_warm) {
-          tma_load_1d(sm.X(), a.Xin + (size_t)base * nx, bx, &bar_io);
-          tma_load_1d(sm.U(), a.Uin + (size_t)base * nu, bu, &bar_io);
-        }
-      }
-      mbar_wait(&bar_io, 0);
+  for (int item = blockIdx.x * WPC + wid; item < nwork;) {
+    const int b = a.refine ? a.q_list[item] : item;
+    ProbState<T> st;
+    const double* xr = nullptr;
+    if (need_xref) xr = fetch_xref(a.xref + (size_t)b * nx, sm.xstg(wid), nx, &bar_x[wid], ph_x, lane);
+    if (need_init) {
+      S.load(xr, need_warm ? a.Xin + (size_t)b * nx : nullptr, need_warm ? a.Uin + (size_t)b * nu : nullptr, a.obstacle, obs);
+      S.init(st);
     } else {
-      for (int i = threadIdx.x; i < nvalid * nx; i += 32 * WPC) {
-        sm.xref()[i] = a.xref[(size_t)base * nx + i];
-        if (need_warm) sm.X()[i] = a.Xin[(size_t)base * nx + i];
-      }
-      if (need_warm) for (int i = threadIdx.x; i < nvalid * nu; i += 32 * WPC) sm.U()[i] = a.Uin[(size_t)base * nu + i];
-      __syncthreads();
-    }
-  }
-
-  // refinement pass: a problem that already converged keeps its result (its staging rows are written back untouched)
-  const bool skip = a.refine && valid && a.status[b] == ST_OPTIMAL;
-  if (need_init) {
-    if (skip) { st.done = 1; st.status = ST_OPTIMAL; st.iters = a.iters ? a.iters[b] : 0; }
-    else if (valid) { S.load(sm.xref(wid), need_warm ? sm.X(wid) : nullptr, need_warm ? sm.U(wid) : nullptr, a.obstacle, obs); S.init(st); }
-    else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
-  } else {
-    // resume: the slab image comes back by one TMA bulk copy per warp, the per-problem scalars by plain loads
-    if (valid) {
+      // resume: the slab image comes back by one TMA bulk copy, the per-problem scalars by plain loads
+      fence_async_smem();
+      __syncwarp();
       if (lane == 0) {
         const uint32_t bytes = (uint32_t)((size_t)L.words * sizeof(T));
         mbar_expect_tx(&bar_w[wid], bytes);
         tma_load_1d(sm.slab(wid), a.slab + (size_t)b * L.words, bytes, &bar_w[wid]);
       }
-      mbar_wait(&bar_w[wid], 0);
+      mbar_wait(&bar_w[wid], ph_w);
+      ph_w ^= 1u;
       st = a.state[b];
 #pragma unroll
       for (int j = 0; j < 6; ++j) obs[j] = a.obs_shift[(size_t)b * 6 + j];
-    } else { st.done = 1; st.status = ST_MAXIT; st.iters = 0; }
-  }
+    }
 
-  if (a.mode != MODE_END && valid && !skip) {
-    for (int it = 0; it < a.n_iter && !st.done; ++it) S.iterate(st);
-  }
+    if (a.mode != MODE_END) {
+      for (int it = 0; it < a.n_iter && !st.done; ++it) S.iterate(st);
+    }
 
-  if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
-    // solution back to float64 row-major (rho is added back in float64), staging -> HBM
-    if (valid && !skip) {
-      S.store(sm.xref(wid), sm.X(wid), sm.U(wid));
+    if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
+      // solution back to float64 row-major (rho is added back in float64): coalesced stores straight from the slab
+      S.store(xr, a.X + (size_t)b * nx, a.U + (size_t)b * nu);
       if (lane == 0) {
         if (a.status) a.status[b] = st.status;
-        if (a.iters) a.iters[b] = st.iters + (a.refine && a.iters ? a.iters[b] : 0);
-      }
-    }
-    if (tile_is_bulk<WPC>(nvalid, nx) && tile_is_bulk<WPC>(nvalid, nu)) {
-      fence_async_smem();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        tma_store_1d(a.X + (size_t)base * nx, sm.X(), (uint32_t)(WPC * nx * sizeof(double)));
-        tma_store_1d(a.U + (size_t)base * nu, sm.U(), (uint32_t)(WPC * nu * sizeof(double)));
-        tma_store_commit_wait();
+        if (a.iters) a.iters[b] = st.iters + (a.refine ? a.iters[b] : 0);
+        // a float32 pass with a refinement queue hands every problem it did not converge to the float64 pass
+        if (a.q_list && !a.refine && st.status != ST_OPTIMAL && st.status != ST_INFEASIBLE_X0) a.q_list[atomicAdd(&a.ctr->q_count, 1)] = b;
       }
     } else {
-      __syncthreads();
-      for (int i = threadIdx.x; i < nvalid * nx; i += 32 * WPC) a.X[(size_t)base * nx + i] = sm.X()[i];
-      for (int i = threadIdx.x; i < nvalid * nu; i += 32 * WPC) a.U[(size_t)base * nu + i] = sm.U()[i];
-    }
-  } else if (valid) {
-    // keep the slab + scalars for the next launch
-    __syncwarp();
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_1d(a.slab + (size_t)b * L.words, sm.slab(wid), (uint32_t)((size_t)L.words * sizeof(T)));
-      tma_store_commit_wait();
-      a.state[b] = st;
+      // keep the slab + scalars for the next launch
+      __syncwarp();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_1d(a.slab + (size_t)b * L.words, sm.slab(wid), (uint32_t)((size_t)L.words * sizeof(T)));
+        tma_store_commit_wait();
+        a.state[b] = st;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) a.obs_shift[(size_t)b * 6 + j] = obs[j];
+        for (int j = 0; j < 6; ++j) a.obs_shift[(size_t)b * 6 + j] = obs[j];
+      }
+      __syncwarp();
+    }
+    if (!a.dynamic) break;
+    int nxt = 0;
+    if (lane == 0) nxt = total_warps + atomicAdd(&a.ctr->next, 1);
+    item = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+  // self-resetting counters: the last warp to leave zeroes what this launch used
+  if ((a.dynamic || a.refine) && lane == 0) {
+    __threadfence();
+    if (atomicAdd(&a.ctr->done, 1) == total_warps - 1) {
+      a.ctr->next = 0; a.ctr->done = 0;
+      if (a.refine) a.ctr->q_count = 0;
     }
   }
 }
 
 // ===================================================================================================== closed loop
+// The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631), one ego per warp, no host round trip
+// between MPC steps (loop body: loop_core.cuh).  Persistent warps like the solve kernel.  Shared memory per warp: the KKT slab
+// + the float64 parameter block and warm-start arrays the reference shifts every step ([N+1][5], [N+1][5], [N][2]).
 template <typename T>
 struct LoopArgs {
   ParamsT<T> P;
-  double obstacle[6];
-  const double* path;      // [Tlen][2]
-  const double* orient;    // [Tlen]
-  const double* x0;        // [B][5]
-  double* traj;            // [B][Tlen][5]
-  double* ctrl;            // [B][Tlen][2]
-  int* status;             // [B][Tlen]
-  int* iters;              // [B][Tlen]
-  double desired_velocity;
-  double l_wb, dt;
-  int B, Tlen;
+  LoopData d;
+  WorkCtr* ctr;
+  int dynamic;
 };
-
-__device__ __forceinline__ void plant_euler(double* x, double u0, double u1, double dt, double l_wb) {
-  // shift_movement: st = x0 + delta_t * f(x0, u[:,0])   (optimizer.py:649-650; KS model configuration.py:364-368)
-  double s, c;
-  sincos(x[4], &s, &c);
-  const double v = x[3], tn = tan(x[2]);
-  x[0] += dt * v * c; x[1] += dt * v * s; x[2] += dt * u0; x[3] += dt * u1; x[4] += dt * v / l_wb * tn;
+static size_t loop_smem_bytes_for(int N, int words, size_t elem, int wpc) {
+  return (size_t)wpc * ((size_t)words * elem + (size_t)(12 * N + 10) * sizeof(double));
 }
 
-// row k+1 of the X_ref block of MPC step i (desired_command_and_trajectory, optimizer.py:657-702, quirk Q8)
-__device__ __forceinline__ void ref_window_row(int i, int k, int N, int Tlen, const double* path, const double* orient, double vdes, double* r) {
-  const int idx = (i >= Tlen - N) ? (k + (Tlen - N)) : (i + k + 1);
-  r[0] = path[2 * idx]; r[1] = path[2 * idx + 1]; r[2] = 0.0; r[3] = vdes; r[4] = orient[idx];
-}
-__device__ __forceinline__ void ref_window_rows(int i, int N, int Tlen, const double* path, const double* orient, double vdes,
-                                                const double* x_now, double* xref /* [N+1][5] */) {
-  for (int j = 0; j < 5; ++j) xref[j] = x_now[j];
-  for (int k = 0; k < N; ++k) ref_window_row(i, k, N, Tlen, path, orient, vdes, xref + 5 * (k + 1));
-}
-
-// The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631) for one ego per warp, no host
-// round trip between MPC steps: solve, record u_0, plant step + warm-start shift, next reference window.
 template <typename T, int WPC, int HM>
 __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __grid_constant__ LoopArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.P.N;
   const WLayout L(N, rec_stride_for(HM));
-  const Smem<T, WPC> sm(smem_raw, N, L.words);
-  const int nu = sm.nu;
-  const int b = blockIdx.x * WPC + wid;
-  if (b >= a.B) return;                                   // whole warp leaves; no CTA-wide barrier below
-  double* my_xref = sm.xref(wid);
-  double* my_X = sm.X(wid);
-  double* my_U = sm.U(wid);
+  const int nx = 5 * (N + 1), nu = 2 * N;
+  double* const stg = reinterpret_cast<double*>(smem_raw + (size_t)WPC * L.words * sizeof(T)) + (size_t)wid * (2 * nx + nu);
+  const int total_warps = gridDim.x * WPC;
   const WarpCtx w;
   T obs[6];
   WarpSolver<T, HM> S(a.P, SlabRef<T>{wid * L.words}, obs, w);
-  ProbState<T> st;
-  double x[5];
-  for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
-  // first parameter block and warm start: the initial state tiled, controls zero (optimizer.py:578-583, quirk Q4)
-  for (int k = lane; k <= N; k += 32)
-    for (int j = 0; j < 5; ++j) { my_xref[5 * k + j] = x[j]; my_X[5 * k + j] = x[j]; }
-  for (int k = lane; k < nu; k += 32) my_U[k] = 0.0;
-  __syncwarp();
-  for (int i = 0; i < a.Tlen; ++i) {
-    if (lane == 0 && a.traj) for (int j = 0; j < 5; ++j) a.traj[((size_t)b * a.Tlen + i) * 5 + j] = x[j];   // quirk Q12
-    S.load(my_xref, my_X, my_U, a.obstacle, obs);
-    S.init(st);
-    for (int it = 0; it < a.P.max_iter && !st.done; ++it) S.iterate(st);
-    S.store(my_xref, my_X, my_U);
-    const double u0 = my_U[0], u1 = my_U[1];
-    if (lane == 0) {
-      if (a.ctrl) { a.ctrl[((size_t)b * a.Tlen + i) * 2] = u0; a.ctrl[((size_t)b * a.Tlen + i) * 2 + 1] = u1; }
-      if (a.status) a.status[(size_t)b * a.Tlen + i] = st.status;
-      if (a.iters) a.iters[(size_t)b * a.Tlen + i] = st.iters;
-    }
-    plant_euler(x, u0, u1, a.dt, a.l_wb);
-    __syncwarp();
-    // shift the warm start one stage, repeating the last (optimizer.py:652-653); lane-strided with a register hop
-    for (int k0 = 0; k0 < N; k0 += 32) {
-      const int k = k0 + lane;
-      double nxt[7];
-      if (k < N) {
-        const int ks = (k + 1 < N) ? k + 1 : N - 1;
-        nxt[5] = my_U[2 * ks]; nxt[6] = my_U[2 * ks + 1];
-        for (int j = 0; j < 5; ++j) nxt[j] = my_X[5 * (k + 1) + j];
-      }
-      __syncwarp();
-      if (k < N) {
-        my_U[2 * k] = nxt[5]; my_U[2 * k + 1] = nxt[6];
-        for (int j = 0; j < 5; ++j) my_X[5 * k + j] = nxt[j];
-      }
-      __syncwarp();
-    }
-    // next window from the new state (optimizer.py:628)
-    if (lane == 0) for (int j = 0; j < 5; ++j) my_xref[j] = x[j];
-    for (int k = lane; k < N; k += 32) ref_window_row(i, k, N, a.Tlen, a.path, a.orient, a.desired_velocity, my_xref + 5 * (k + 1));
-    __syncwarp();
+  for (int b = blockIdx.x * WPC + wid; b < a.d.B;) {
+    closed_loop_ego<T, HM>(S, a.d, b, stg, stg + nx, stg + 2 * nx, obs, a.P.max_iter);
+    if (!a.dynamic) break;
+    int nxt = 0;
+    if (lane == 0) nxt = total_warps + atomicAdd(&a.ctr->next, 1);
+    b = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+  if (a.dynamic && lane == 0) {
+    __threadfence();
+    if (atomicAdd(&a.ctr->done, 1) == total_warps - 1) { a.ctr->next = 0; a.ctr->done = 0; }
   }
 }
 
@@ -349,16 +306,20 @@ __global__ void build_ref_window_kernel(int i, int Tlen, const double* path, con
 
 // ===================================================================================================== handle
 #define MPCB200_HOST_STREAMS 4
+struct KernelPlan {     // launch shape of one kernel family (solve / refinement / closed loop) for this handle
+  int wpc;              // warps (= problems) per CTA
+  size_t smem;          // dynamic shared memory per CTA
+  int max_ctas;         // resident CTAs on the device (SM count x occupancy): the persistent grid never exceeds it
+};
 struct mpcb200_handle {
   mpcb200_config cfg;
-  int wpc;              // warps (= problems) per CTA
-  size_t smem_bytes;
-  int wpc64;            // same for the float64 refinement pass of a float32 handle (cfg.refine_f64)
-  size_t smem64;
+  KernelPlan solve, refine, loop;
   int words;            // slab words per problem
   void* slab;           // global slab image [max_batch][words] (stepwise mode), allocated on first use
   void* state;
   void* obs_shift;
+  WorkCtr* ctr;         // device work counters (zeroed at create, self-resetting afterwards)
+  int* q_list;          // [max_batch] refinement queue (refine_f64 handles)
   size_t elem;          // sizeof(T)
   int64_t launches;
   // stepwise-mode context
@@ -382,49 +343,100 @@ static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev; bool switched;
+  explicit DeviceGuard(int dev) : prev(-1), switched(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+static int grid_for(const KernelPlan& k, int nwork) {
+  const int want = (nwork + k.wpc - 1) / k.wpc;
+  return want < k.max_ctas ? want : k.max_ctas;
+}
+
 template <typename T, int WPC, int HM>
-static cudaError_t launch_solve(mpcb200_handle* h, const SolveArgs<T>& a, cudaStream_t s, size_t smem) {
-  const int ctas = (a.B + WPC - 1) / WPC;
-  mpc_warp_solve_kernel<T, WPC, HM><<<ctas, 32 * WPC, smem, s>>>(a);
+static cudaError_t launch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
+  const int ctas = grid_for(k, nwork);
+  a.dynamic = (a.refine || nwork > ctas * WPC) ? 1 : 0;
+  mpc_warp_solve_kernel<T, WPC, HM><<<ctas, 32 * WPC, k.smem, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
 template <typename T, int WPC, int HM>
-static cudaError_t launch_loop(mpcb200_handle* h, const LoopArgs<T>& a, cudaStream_t s) {
-  const int ctas = (a.B + WPC - 1) / WPC;
-  mpc_warp_closed_loop_kernel<T, WPC, HM><<<ctas, 32 * WPC, h->smem_bytes, s>>>(a);
+static cudaError_t launch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t s) {
+  const int ctas = grid_for(h->loop, a.d.B);
+  a.dynamic = (a.d.B > ctas * WPC) ? 1 : 0;
+  mpc_warp_closed_loop_kernel<T, WPC, HM><<<ctas, 32 * WPC, h->loop.smem, s>>>(a);
   h->launches++;
   return cudaGetLastError();
 }
 
-// kernel instantiations: arithmetic type x problems per CTA (2, or 1 when the slab of a long horizon leaves no room for
-// two) x Hessian mode
+// kernel instantiations: arithmetic type x problems per CTA (1, 2, 4) x Hessian mode
+#define MPC_DISPATCH_WPC(WPCV, ...)                          \
+  switch (WPCV) {                                            \
+    case 4: { constexpr int W = 4; __VA_ARGS__; } break;     \
+    case 2: { constexpr int W = 2; __VA_ARGS__; } break;     \
+    default: { constexpr int W = 1; __VA_ARGS__; } break;    \
+  }
 template <typename T>
-static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s, int wpc, size_t smem) {
+static cudaError_t dispatch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
   const bool ex = a.P.hessian == HESS_EXACT;
-  if (wpc == 2) return ex ? launch_solve<T, 2, HESS_EXACT>(h, a, s, smem) : launch_solve<T, 2, HESS_GN>(h, a, s, smem);
-  return ex ? launch_solve<T, 1, HESS_EXACT>(h, a, s, smem) : launch_solve<T, 1, HESS_GN>(h, a, s, smem);
+  cudaError_t e = cudaSuccess;
+  MPC_DISPATCH_WPC(k.wpc, e = ex ? launch_solve<T, W, HESS_EXACT>(h, a, s, k, nwork) : launch_solve<T, W, HESS_GN>(h, a, s, k, nwork));
+  return e;
 }
 template <typename T>
 static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t s) {
   const bool ex = a.P.hessian == HESS_EXACT;
-  if (h->wpc == 2) return ex ? launch_loop<T, 2, HESS_EXACT>(h, a, s) : launch_loop<T, 2, HESS_GN>(h, a, s);
-  return ex ? launch_loop<T, 1, HESS_EXACT>(h, a, s) : launch_loop<T, 1, HESS_GN>(h, a, s);
+  cudaError_t e = cudaSuccess;
+  MPC_DISPATCH_WPC(h->loop.wpc, e = ex ? launch_loop<T, W, HESS_EXACT>(h, a, s) : launch_loop<T, W, HESS_GN>(h, a, s));
+  return e;
 }
 
-// opt the handle's kernel instantiations in to their dynamic shared memory size (once, at create)
-template <typename T, int WPC>
-static cudaError_t configure_kernels_t(size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC, HESS_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_warp_solve_kernel<T, WPC, HESS_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC, HESS_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_warp_closed_loop_kernel<T, WPC, HESS_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// Opt every instantiation this handle can launch in to the device's FULL opt-in shared memory (a property of the function on
+// the device, shared by all handles: never a per-handle size, so one handle cannot lower another's limit), and ask the
+// occupancy calculator how many CTAs of the handle's size stay resident.
+template <typename K>
+static cudaError_t plan_kernel(K kern, int wpc, size_t smem, int optin, int sms, int* max_ctas) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * wpc, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  *max_ctas = occ * sms;
+  return cudaSuccess;
+}
+template <typename T>
+static cudaError_t plan_solve(KernelPlan& k, bool exact, int optin, int sms) {
+  cudaError_t e = cudaSuccess;
+  MPC_DISPATCH_WPC(k.wpc, e = exact ? plan_kernel(mpc_warp_solve_kernel<T, W, HESS_EXACT>, W, k.smem, optin, sms, &k.max_ctas)
+                                    : plan_kernel(mpc_warp_solve_kernel<T, W, HESS_GN>, W, k.smem, optin, sms, &k.max_ctas));
   return e;
 }
 template <typename T>
-static cudaError_t configure_kernels(int wpc, size_t smem) {
-  if (wpc == 2) return configure_kernels_t<T, 2>(smem);
-  return configure_kernels_t<T, 1>(smem);
+static cudaError_t plan_loop(KernelPlan& k, bool exact, int optin, int sms) {
+  cudaError_t e = cudaSuccess;
+  MPC_DISPATCH_WPC(k.wpc, e = exact ? plan_kernel(mpc_warp_closed_loop_kernel<T, W, HESS_EXACT>, W, k.smem, optin, sms, &k.max_ctas)
+                                    : plan_kernel(mpc_warp_closed_loop_kernel<T, W, HESS_GN>, W, k.smem, optin, sms, &k.max_ctas));
+  return e;
+}
+// problems per CTA: the preferred count, else the largest of 4 / 2 / 1 whose CTA fits the opt-in shared memory
+static bool choose_wpc(KernelPlan& k, int pref, size_t (*bytes)(int, int, size_t, int), int N, int words, size_t elem, size_t smem_max) {
+  const int cand[4] = {pref, 4, 2, 1};
+  for (int i = 0; i < 4; ++i) {
+    const int wpc = cand[i];
+    if (wpc != 1 && wpc != 2 && wpc != 4) continue;
+    const size_t need = bytes(N, words, elem, wpc);
+    if (need + 1024 <= smem_max) { k.wpc = wpc; k.smem = need; return true; }
+  }
+  return false;
 }
 
 static int ensure_stepwise_scratch(mpcb200_handle* h) {
@@ -441,6 +453,7 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
                     int B, cudaStream_t s, int cold = 0, const double* Xin = nullptr, const double* Uin = nullptr) {
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  if (((uintptr_t)xref | (uintptr_t)X | (uintptr_t)U | (uintptr_t)Xin | (uintptr_t)Uin) & 7u) { h->err = "float64 arrays must be 8-byte aligned"; return -2; }
   if (mode != MODE_ONESHOT) { int rc = ensure_stepwise_scratch(h); if (rc) return rc; }
   SolveArgs<T> a;
   a.P = params_from_config<T>(h->cfg);
@@ -448,26 +461,53 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
   a.Xin = Xin ? Xin : X; a.Uin = Uin ? Uin : U;
   a.slab = (T*)h->slab; a.state = (ProbState<T>*)h->state; a.obs_shift = (T*)h->obs_shift;
-  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold; a.refine = 0;
-  cudaError_t e = dispatch_solve<T>(h, a, s, h->wpc, h->smem_bytes);
+  a.ctr = h->ctr;
+  // a float32 handle with cfg.refine_f64 queues what it did not converge for the float64 pass that follows (fused mode only)
+  a.q_list = (mode == MODE_ONESHOT && sizeof(T) == 4 && h->cfg.refine_f64 && status) ? h->q_list : nullptr;
+  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold; a.refine = 0; a.dynamic = 0;
+  cudaError_t e = dispatch_solve<T>(h, a, s, h->solve, B);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel launch", e);
   return 0;
 }
 
-// second pass of a float32 handle with cfg.refine_f64: float64 arithmetic (float32 tolerances) on the instances that did
-// not reach status 1, warm-started from their float32 result
+// second pass of a float32 handle with cfg.refine_f64: float64 arithmetic (float32 tolerances) on the instances the float32
+// pass queued (status other than 1), warm-started from their float32 result.  A small persistent grid: the queue is usually
+// short or empty (then every warp leaves after one load).
 static int refine_pass(mpcb200_handle* h, const double* xref, double* X, double* U, int* status, int* iters, int B, cudaStream_t s) {
-  if (!status) { h->err = "refine_f64 needs a status buffer"; return -2; }
+  if (!status) return 0;                                // without a status buffer nothing was queued
   SolveArgs<double> a;
   a.P = params_from_config<double>(h->cfg);
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
   a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
   a.Xin = X; a.Uin = U;
   a.slab = nullptr; a.state = nullptr; a.obs_shift = nullptr;
-  a.B = B; a.mode = MODE_ONESHOT; a.n_iter = h->cfg.max_iter; a.cold = 0; a.refine = 1;
-  cudaError_t e = dispatch_solve<double>(h, a, s, h->wpc64, h->smem64);
+  a.ctr = h->ctr; a.q_list = h->q_list;
+  a.B = B; a.mode = MODE_ONESHOT; a.n_iter = h->cfg.max_iter; a.cold = 0; a.refine = 1; a.dynamic = 1;
+  cudaError_t e = dispatch_solve<double>(h, a, s, h->refine, B);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel<double> (refinement) launch", e);
   return 0;
+}
+
+// one solve (+ the float64 refinement pass of a refine_f64 handle) with separate warm-start-in and result-out arrays
+static int solve_io(mpcb200_handle* h, const double* xref, const double* Xin, const double* Uin, double* X, double* U,
+                    int32_t* status, int32_t* iters, int32_t B, cudaStream_t s, int cold) {
+  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin);
+  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin);
+  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, xref, X, U, status, iters, B, s);
+  return rc;
+}
+
+template <typename T>
+static cudaError_t closed_loop_t(mpcb200_handle* h, int32_t iter_length, const double* d_path, const double* d_orientation, double desired_velocity,
+                                 const double* d_x0, double* d_traj, double* d_ctrl, int32_t* d_status, int32_t* d_iters, int32_t B, cudaStream_t s) {
+  LoopArgs<T> a;
+  a.P = params_from_config<T>(h->cfg);
+  for (int i = 0; i < 6; ++i) a.d.obstacle[i] = h->cfg.obstacle[i];
+  a.d.path = d_path; a.d.orient = d_orientation; a.d.x0 = d_x0; a.d.traj = d_traj; a.d.ctrl = d_ctrl; a.d.status = d_status; a.d.iters = d_iters;
+  a.d.desired_velocity = desired_velocity; a.d.l_wb = h->cfg.l_wb; a.d.dt = h->cfg.dt; a.d.B = B; a.d.Tlen = iter_length;
+  a.d.warm_duals = h->cfg.warm_duals;
+  a.ctr = h->ctr; a.dynamic = 0;
+  return dispatch_loop<T>(h, a, s);
 }
 
 extern "C" {
@@ -486,40 +526,44 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) { fail(nullptr, "no CUDA device (libmpcb200 has no CPU path)", e); return -3; }
-  CK(cudaSetDevice(cfg->device));
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "cfg.device out of range"; return -2; }
+  DeviceGuard guard(cfg->device);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major < 9) { g_create_err = "libmpcb200 needs TMA bulk copies (sm_90+); built for sm_100a"; return -3; }
   h = new (std::nothrow) mpcb200_handle();
   if (!h) { g_create_err = "out of host memory"; return -4; }
   h->cfg = *cfg;
-  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr;
+  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr; h->ctr = nullptr; h->q_list = nullptr;
   h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
   h->sw_xref = nullptr; h->sw_B = 0;
-  const WLayout L(cfg->N, rec_stride_for(cfg->hessian == MPCB200_HESS_EXACT ? HESS_EXACT : HESS_GN));
+  const bool exact = cfg->hessian == MPCB200_HESS_EXACT;
+  const WLayout L(cfg->N, rec_stride_for(exact ? HESS_EXACT : HESS_GN));
   h->words = L.words;
-  h->elem = cfg->precision == MPCB200_F64 ? 8 : 4;
+  const bool f64 = cfg->precision == MPCB200_F64;
+  h->elem = f64 ? 8 : 4;
   const size_t smem_max = prop.sharedMemPerBlockOptin;   // 227 KB on B200
-  const size_t reserve = 1024;
-  h->wpc = 0;
-  int wpc_pref = 2;
-  if (const char* ev = getenv("MPCB200_WPC")) { const int v = atoi(ev); if (v == 1 || v == 2) wpc_pref = v; }   // tuning knob
-  for (int wpc : {wpc_pref, 2, 1}) {
-    const size_t need = smem_bytes_for(cfg->N, L.words, h->elem, wpc);
-    if (need + reserve <= smem_max) { h->wpc = wpc; h->smem_bytes = need; break; }
+  const int optin = (int)prop.sharedMemPerBlockOptin, sms = prop.multiProcessorCount;
+  const int pref = (cfg->warps_per_cta == 1 || cfg->warps_per_cta == 2 || cfg->warps_per_cta == 4) ? cfg->warps_per_cta : 2;
+  if (!choose_wpc(h->solve, pref, smem_bytes_for, cfg->N, L.words, h->elem, smem_max) ||
+      !choose_wpc(h->loop, pref, loop_smem_bytes_for, cfg->N, L.words, h->elem, smem_max)) {
+    g_create_err = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2;
   }
-  if (!h->wpc) { g_create_err = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2; }
-  e = (cfg->precision == MPCB200_F64) ? configure_kernels<double>(h->wpc, h->smem_bytes) : configure_kernels<float>(h->wpc, h->smem_bytes);
-  if (e != cudaSuccess) { fail(nullptr, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e); delete h; return -1; }
-  h->wpc64 = 0; h->smem64 = 0;
-  if (cfg->precision == MPCB200_F32 && cfg->refine_f64) {
-    for (int wpc : {2, 1}) {
-      const size_t need = smem_bytes_for(cfg->N, L.words, 8, wpc);
-      if (need + reserve <= smem_max) { h->wpc64 = wpc; h->smem64 = need; break; }
+  e = f64 ? plan_solve<double>(h->solve, exact, optin, sms) : plan_solve<float>(h->solve, exact, optin, sms);
+  if (e == cudaSuccess) e = f64 ? plan_loop<double>(h->loop, exact, optin, sms) : plan_loop<float>(h->loop, exact, optin, sms);
+  if (e != cudaSuccess) { fail(nullptr, "kernel configuration (shared memory opt-in / occupancy)", e); delete h; return -1; }
+  h->refine.wpc = 0;
+  if (!f64 && cfg->refine_f64) {
+    if (!choose_wpc(h->refine, 1, smem_bytes_for, cfg->N, L.words, 8, smem_max)) {
+      g_create_err = "horizon too long for the float64 refinement pass"; delete h; return -2;
     }
-    if (!h->wpc64) { g_create_err = "horizon too long for the float64 refinement pass"; delete h; return -2; }
-    e = configure_kernels<double>(h->wpc64, h->smem64);
-    if (e != cudaSuccess) { fail(nullptr, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e); delete h; return -1; }
+    e = plan_solve<double>(h->refine, exact, optin, sms);
+    if (e != cudaSuccess) { fail(nullptr, "kernel configuration (float64 refinement)", e); delete h; return -1; }
+    if (h->refine.max_ctas > sms) h->refine.max_ctas = sms;          // the queue is short: one CTA per SM is plenty
+    if (cudaMalloc(&h->q_list, (size_t)cfg->max_batch * sizeof(int)) != cudaSuccess) { fail(nullptr, "cudaMalloc(refinement queue)", cudaGetLastError()); delete h; return -1; }
+  }
+  if (cudaMalloc(&h->ctr, sizeof(WorkCtr)) != cudaSuccess || cudaMemset(h->ctr, 0, sizeof(WorkCtr)) != cudaSuccess) {
+    fail(nullptr, "cudaMalloc(work counters)", cudaGetLastError()); cudaFree(h->q_list); delete h; return -1;
   }
   *out = h;
   return 0;
@@ -527,7 +571,8 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
 
 void mpcb200_destroy(mpcb200_handle* h) {
   if (!h) return;
-  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift);
+  DeviceGuard guard(h->cfg.device);
+  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift); cudaFree(h->ctr); cudaFree(h->q_list);
   if (h->h_pin) for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) cudaStreamDestroy(h->hs[i]);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -537,25 +582,20 @@ void mpcb200_destroy(mpcb200_handle* h) {
 int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters,
                   int32_t B, void* stream) {
   if (!h) return -2;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
-  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s);
-  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, d_xref, d_X, d_U, d_status, d_iters, B, s);
-  return rc;
+  DeviceGuard guard(h->cfg.device);
+  return solve_io(h, d_xref, nullptr, nullptr, d_X, d_U, d_status, d_iters, B, (cudaStream_t)stream, 0);
 }
 
 int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters,
                        int32_t B, void* stream) {
   if (!h) return -2;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
-  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, d_xref, d_X, d_U, d_status, d_iters, B, s, 1);
-  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, d_xref, d_X, d_U, d_status, d_iters, B, s);
-  return rc;
+  DeviceGuard guard(h->cfg.device);
+  return solve_io(h, d_xref, nullptr, nullptr, d_X, d_U, d_status, d_iters, B, (cudaStream_t)stream, 1);
 }
 
 int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X, const double* d_U, int32_t B, void* stream) {
   if (!h) return -2;
+  DeviceGuard guard(h->cfg.device);
   h->sw_xref = d_xref; h->sw_B = B;
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_BEGIN, 0, d_xref, (double*)d_X, (double*)d_U, nullptr, nullptr, B, s);
@@ -564,6 +604,7 @@ int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X
 
 int mpcb200_sqp_iter(mpcb200_handle* h, int32_t n_iter, void* stream) {
   if (!h || !h->sw_xref) { if (h) h->err = "sqp_iter without sqp_begin"; return -2; }
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ITER, n_iter, h->sw_xref, nullptr, nullptr, nullptr, nullptr, h->sw_B, s);
   return do_solve<float>(h, MODE_ITER, n_iter, h->sw_xref, nullptr, nullptr, nullptr, nullptr, h->sw_B, s);
@@ -571,6 +612,7 @@ int mpcb200_sqp_iter(mpcb200_handle* h, int32_t n_iter, void* stream) {
 
 int mpcb200_sqp_end(mpcb200_handle* h, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters, void* stream) {
   if (!h || !h->sw_xref) { if (h) h->err = "sqp_end without sqp_begin"; return -2; }
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   if (h->cfg.precision == MPCB200_F64) rc = do_solve<double>(h, MODE_END, 0, h->sw_xref, d_X, d_U, d_status, d_iters, h->sw_B, s);
@@ -582,6 +624,7 @@ int mpcb200_sqp_end(mpcb200_handle* h, double* d_X, double* d_U, int32_t* d_stat
 int mpcb200_plant_step_shift(mpcb200_handle* h, double* d_x, double* d_U, double* d_X, double* d_u_applied, int32_t B, void* stream) {
   if (!h) return -2;
   if (B <= 0) return 0;
+  DeviceGuard guard(h->cfg.device);
   plant_step_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_x, d_U, d_X, d_u_applied, B, h->cfg.N, h->cfg.dt, h->cfg.l_wb);
   h->launches++;
   cudaError_t e = cudaGetLastError();
@@ -594,6 +637,7 @@ int mpcb200_build_ref_window(mpcb200_handle* h, int32_t i, int32_t iter_length, 
   if (!h) return -2;
   if (B <= 0) return 0;
   if (h->cfg.N > iter_length) { h->err = "predict_horizon exceeds iter_length"; return -2; }
+  DeviceGuard guard(h->cfg.device);
   build_ref_window_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(i, iter_length, d_path, d_orientation, desired_velocity, d_x,
                                                                              d_xref, B, h->cfg.N);
   h->launches++;
@@ -608,22 +652,10 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
   if (h->cfg.N > iter_length) { h->err = "predict_horizon exceeds iter_length"; return -2; }
-  cudaError_t e;
-  if (h->cfg.precision == MPCB200_F64) {
-    LoopArgs<double> a;
-    a.P = params_from_config<double>(h->cfg);
-    for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
-    a.path = d_path; a.orient = d_orientation; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
-    a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
-    e = dispatch_loop<double>(h, a, (cudaStream_t)stream);
-  } else {
-    LoopArgs<float> a;
-    a.P = params_from_config<float>(h->cfg);
-    for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
-    a.path = d_path; a.orient = d_orientation; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
-    a.desired_velocity = desired_velocity; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = iter_length;
-    e = dispatch_loop<float>(h, a, (cudaStream_t)stream);
-  }
+  DeviceGuard guard(h->cfg.device);
+  const cudaError_t e = (h->cfg.precision == MPCB200_F64)
+      ? closed_loop_t<double>(h, iter_length, d_path, d_orientation, desired_velocity, d_x0, d_traj, d_ctrl, d_status, d_iters, B, (cudaStream_t)stream)
+      : closed_loop_t<float>(h, iter_length, d_path, d_orientation, desired_velocity, d_x0, d_traj, d_ctrl, d_status, d_iters, B, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(h, "mpc_closed_loop_kernel launch", e);
   return 0;
 }
@@ -637,21 +669,13 @@ static void* mapped_alias(const void* p) {
   return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
 }
 
-// one solve (+ optional float64 refinement) with separate warm-start-in and result-out arrays
-static int solve_io(mpcb200_handle* h, const double* xref, const double* Xin, const double* Uin, double* X, double* U,
-                    int32_t* status, int32_t* iters, int32_t B, cudaStream_t s, int cold) {
-  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin);
-  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin);
-  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, xref, X, U, status, iters, B, s);
-  return rc;
-}
-
 int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U, double* h_X_out, double* h_U_out,
                        int32_t* h_status, int32_t* h_iters, int32_t B) {
   if (!h) return -2;
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
   if (!h_xref || !h_X_out || !h_U_out || (!h_X != !h_U)) { h->err = "null host buffer"; return -2; }
+  DeviceGuard guard(h->cfg.device);
   const bool cold = !h_X;                               // no warm start: nothing but xref is uploaded
   const int N = h->cfg.N;
   const size_t nx = (size_t)5 * (N + 1), nu = (size_t)2 * N, mb = h->cfg.max_batch;
@@ -659,11 +683,11 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
     CK(cudaMallocHost(&h->h_pin, 2 * mb * 4));
     for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
   }
-  // ---- zero-copy route: every data buffer is pinned host memory the device can address.  ONE launch; the kernel's TMA
-  // bulk copies read xref (+ warm start) from and write X / U to host memory directly over PCIe, so problem b's transfer
-  // overlaps the other problems' iterations inside the kernel and no staging copy or extra launch is on the critical path.
-  const char* staged_env = getenv("MPCB200_HOST_STAGED");   // tuning knob: force the staged pipeline below
-  if (!(staged_env && atoi(staged_env))) {
+  // ---- zero-copy route: every data buffer is pinned host memory the device can address.  ONE launch (two with the float64
+  // refinement pass); the warps' TMA bulk copies read xref from, and their coalesced stores write X / U to, host memory
+  // directly over PCIe, so problem b's transfer overlaps the other problems' iterations inside the kernel and no staging
+  // copy or extra launch is on the critical path.
+  if (h->cfg.host_route != 1) {
     const double* m_xref = (const double*)mapped_alias(h_xref);
     double* m_Xo = (double*)mapped_alias(h_X_out);
     double* m_Uo = (double*)mapped_alias(h_U_out);
@@ -686,14 +710,16 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
     CK(cudaMalloc(&h->d_status, mb * 4)); CK(cudaMalloc(&h->d_iters, mb * 4));
   }
   // Chunked pipeline over a few streams: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 run under the solve
-  // of chunk c (with pinned host buffers; pageable ones still work, the copies just serialise).  Chunks are even-sized
-  // so every CTA keeps a full 2-problem tile.
+  // of chunk c (with pinned host buffers; pageable ones still work, the copies just serialise).  The work counters and the
+  // refinement queue belong to ONE launch at a time, so a handle whose launches use them (refine_f64, or chunks larger than
+  // the resident grid) runs its chunks on one stream.
   int nchunk = (B >= 4096) ? MPCB200_HOST_STREAMS : (B >= 512 ? 2 : 1);   // small batches are latency-bound: fewer, larger chunks
-  if (const char* ev = getenv("MPCB200_HOST_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= MPCB200_HOST_STREAMS) nchunk = v; }   // tuning knob
-  int per = ((B + nchunk - 1) / nchunk + 1) & ~1;
+  if (h->cfg.host_chunks >= 1 && h->cfg.host_chunks <= MPCB200_HOST_STREAMS) nchunk = h->cfg.host_chunks;
+  const int per = (B + nchunk - 1) / nchunk;
+  const bool one_stream = (h->cfg.precision == MPCB200_F32 && h->cfg.refine_f64) || per > h->solve.max_ctas * h->solve.wpc;
   for (int c = 0, lo = 0; lo < B; ++c, lo += per) {
     const int n = (B - lo < per) ? (B - lo) : per;
-    cudaStream_t s = h->hs[c % MPCB200_HOST_STREAMS];
+    cudaStream_t s = h->hs[one_stream ? 0 : c % MPCB200_HOST_STREAMS];
     CK(cudaMemcpyAsync(h->d_xref + lo * nx, h_xref + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
     if (!cold) {
       CK(cudaMemcpyAsync(h->d_X + lo * nx, h_X + lo * nx, n * nx * 8, cudaMemcpyHostToDevice, s));
@@ -715,6 +741,6 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
 
 int64_t mpcb200_launch_count(const mpcb200_handle* h) { return h ? h->launches : 0; }
 int32_t mpcb200_workspace_words(const mpcb200_handle* h) { return h ? h->words : 0; }
-int32_t mpcb200_slab_in_smem(const mpcb200_handle* h) { return h ? h->wpc : 0; }
+int32_t mpcb200_slab_in_smem(const mpcb200_handle* h) { return h ? h->solve.wpc : 0; }
 
 }  // extern "C"

@@ -225,24 +225,36 @@ struct WarpSolver {
   }
 
   // ---------------------------------------------------------------- problem I/O (float64 row-major arrays of ONE problem)
-  // xref [N+1][5] (row 0 = pinned state), Xin [N+1][5], Uin [N][2] (either may be null: cold start = the reference's
-  // step-0 guess, X_0 tiled and zero controls, optimizer.py:578-583).  Differences are formed in float64, then rounded.
+  // xref [N+1][5] (row 0 = pinned state) is read lane = STAGE (on the device it sits in the warp's shared-memory staging,
+  // filled by one TMA bulk copy); the warm start Xin [N+1][5], Uin [N][2] (either may be null: cold start = the reference's
+  // step-0 guess, X_0 tiled and zero controls, optimizer.py:578-583) is read lane = ELEMENT straight from global / pinned host
+  // memory: coalesced 256-byte requests, every byte touched once.  Differences are formed in float64, then rounded.
   MPC_HD void load(const double* xref, const double* Xin, const double* Uin, const double* obstacle_abs, T* obs_out) const {
     const int N = P.N;
     const double ox = xref[0], oy = xref[1];
     for (int j = 0; j < 3; ++j) { obs_out[2 * j] = (T)(obstacle_abs[2 * j] - ox); obs_out[2 * j + 1] = (T)(obstacle_abs[2 * j + 1] - oy); }
     for (int k = lane; k <= N; k += 32) {
       const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
-      const double* xin = (k == 0 || !Xin) ? xref : (Xin + 5 * k);   // stage 0 is pinned to X_ref[:,0]; no warm start = X_0 tiled
       sx(k, S_XR + 0) = (T)(rho[0] - ox); sx(k, S_XR + 1) = (T)(rho[1] - oy);
       sx(k, S_XR + 2) = (T)rho[2]; sx(k, S_XR + 3) = (T)rho[3]; sx(k, S_XR + 4) = (T)rho[4];
-      for (int j = 0; j < 5; ++j) sx(k, S_XT + j) = (T)(xin[j] - rho[j]);
+      if (k == 0 || !Xin) {                                           // stage 0 is pinned to X_ref[:,0]; no warm start = X_0 tiled
+        for (int j = 0; j < 5; ++j) sx(k, S_XT + j) = (T)(xref[j] - rho[j]);
+      }
       if (k < N) {
         const double* rho1 = xref + 5 * ((k + 2 < N) ? (k + 2) : N);
         rc(k, R_CP) = (T)(rho[0] - rho1[0]); rc(k, R_CP + 1) = (T)(rho[1] - rho1[1]);
-        rc(k, R_U) = Uin ? (T)Uin[2 * k] : T(0); rc(k, R_U + 1) = Uin ? (T)Uin[2 * k + 1] : T(0);
+        if (!Uin) { rc(k, R_U) = T(0); rc(k, R_U + 1) = T(0); }
         rc(k, R_ZERO) = T(0); rc(k, R_ONE) = T(1);
       }
+    }
+    if (Xin) {
+      for (int e = 5 + lane; e < 5 * (N + 1); e += 32) {
+        const int k = e / 5, j = e - 5 * k;
+        sx(k, S_XT + j) = (T)(Xin[e] - xref[5 * ((k + 1 < N) ? (k + 1) : N) + j]);
+      }
+    }
+    if (Uin) {
+      for (int e = lane; e < 2 * N; e += 32) rc(e >> 1, R_U + (e & 1)) = (T)Uin[e];
     }
     w.sync();
     if (P.init_rollout) {
@@ -251,7 +263,7 @@ struct WarpSolver {
       double x[5];
       for (int j = 0; j < 5; ++j) x[j] = xref[j];
       for (int k = 0; k < N; ++k) {
-        const double u0 = Uin ? Uin[2 * k] : 0.0, u1 = Uin ? Uin[2 * k + 1] : 0.0;
+        const double u0 = (double)rc(k, R_U), u1 = (double)rc(k, R_U + 1);
         const double v = x[3], sn = sin(x[4]), cs = cos(x[4]), tn = tan(x[2]);
         x[0] += (double)P.dt * v * cs; x[1] += (double)P.dt * v * sn; x[2] += (double)P.dt * u0; x[3] += (double)P.dt * u1;
         x[4] += (double)P.dt * v * tn / (double)P.l_wb;
@@ -263,14 +275,16 @@ struct WarpSolver {
       w.sync();
     }
   }
+  // solution out, lane = ELEMENT: coalesced stores straight from the slab to global / pinned host memory (rho is added back
+  // in float64 from the xref block)
   MPC_HD void store(const double* xref, double* Xout, double* Uout) const {
     const int N = P.N;
     w.sync();
-    for (int k = lane; k <= N; k += 32) {
-      const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
-      for (int j = 0; j < 5; ++j) Xout[5 * k + j] = (k == 0) ? xref[j] : ((double)sx(k, S_XT + j) + rho[j]);
-      if (k < N) { Uout[2 * k] = (double)rc(k, R_U); Uout[2 * k + 1] = (double)rc(k, R_U + 1); }
+    for (int e = lane; e < 5 * (N + 1); e += 32) {
+      const int k = e / 5, j = e - 5 * k;
+      Xout[e] = (k == 0) ? xref[j] : ((double)sx(k, S_XT + j) + xref[5 * ((k + 1 < N) ? (k + 1) : N) + j]);
     }
+    for (int e = lane; e < 2 * N; e += 32) Uout[e] = (double)rc(e >> 1, R_U + (e & 1));
     w.sync();
   }
 
@@ -340,6 +354,209 @@ struct WarpSolver {
         const T s = m_max(c, kp * m_max(T(1), P.r_sum));
         rc(k, R_S + j) = s;
         rc(k, R_V + V_OB0 + j) = mu * m_rcp(s);
+      }
+      for (int j = 0; j < 5; ++j) rc(k, R_DX + j) = T(0);
+      rc(k, R_DU) = T(0); rc(k, R_DU + 1) = T(0);
+    }
+    w.sync();
+  }
+
+  // ---------------------------------------------------------------- dual warm start across MPC steps
+  // The dual half of shift_movement (optimizer.py:652-653 shifts only the primal arrays; IPOPT restarts its multipliers
+  // every step): inequality multipliers and obstacle slacks of stage k+1 become those of stage k, the last stage is repeated.
+  MPC_HD void shift_duals() const {
+    const int N = P.N;
+    for (int k0 = 0; k0 < N; k0 += 32) {
+      const int k = k0 + lane;
+      T v[NV + 3];
+      if (k < N) {
+        const int ks = (k + 1 < N) ? k + 1 : N - 1;
+#pragma unroll
+        for (int j = 0; j < NV + 3; ++j) v[j] = rc(ks, R_V + j);          // R_V (11) and R_S (3) are adjacent
+      }
+      w.sync();
+      if (k < N) {
+#pragma unroll
+        for (int j = 0; j < NV + 3; ++j) rc(k, R_V + j) = v[j];
+      }
+      w.sync();
+    }
+  }
+  // New parameter block for a slab that keeps the previous MPC step's solution (controls, slacks, multipliers): only the
+  // reference-derived words and the pinned stage are rewritten.
+  MPC_HD void load_reference(const double* xref, const double* obstacle_abs, T* obs_out) const {
+    const int N = P.N;
+    const double ox = xref[0], oy = xref[1];
+    for (int j = 0; j < 3; ++j) { obs_out[2 * j] = (T)(obstacle_abs[2 * j] - ox); obs_out[2 * j + 1] = (T)(obstacle_abs[2 * j + 1] - oy); }
+    for (int k = lane; k <= N; k += 32) {
+      const double* rho = xref + 5 * ((k + 1 < N) ? (k + 1) : N);
+      sx(k, S_XR + 0) = (T)(rho[0] - ox); sx(k, S_XR + 1) = (T)(rho[1] - oy);
+      sx(k, S_XR + 2) = (T)rho[2]; sx(k, S_XR + 3) = (T)rho[3]; sx(k, S_XR + 4) = (T)rho[4];
+      if (k == 0) { for (int j = 0; j < 5; ++j) sx(0, S_XT + j) = (T)(xref[j] - rho[j]); }
+      if (k < N) {
+        const double* rho1 = xref + 5 * ((k + 2 < N) ? (k + 2) : N);
+        rc(k, R_CP) = (T)(rho[0] - rho1[0]); rc(k, R_CP + 1) = (T)(rho[1] - rho1[1]);
+      }
+    }
+    w.sync();
+  }
+  // Primal warm start of an MPC step from the previous step's controls (still in the slab).  Two candidate control
+  // sequences -- the previous plan shifted one stage (shift_movement's guess, optimizer.py:652: right when the plan is
+  // executed as predicted) and the previous plan as it is (right when the window is frozen, quirk Q8, or when the pinned
+  // stage's friction box clamps u_0 every step, quirks Q3 / Q7) -- are rolled out from the new pinned state by two lanes
+  // at once; the one with the lower cost + bound violation is kept, its single-shooting states become the start point (zero
+  // dynamics defects), and controls / slacks / multipliers are shifted to match.  Returns the chosen shift (0 or 1).
+  MPC_HD int warm_primal(const ProbState<T>& st0) const {
+    const int N = P.N;
+    const int c = lane & 1;                       // candidate of this lane: shift by c stages
+    T a0_lo, a0_hi;
+    {
+      const T de0 = xa(0, 2), v0 = xa(0, 3);
+      const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
+      const T amax0 = m_sqrt(m_max(P.a_max - s0, T(1e-12)));
+      a0_hi = m_min(amax0, P.a_max); a0_lo = -amax0;
+    }
+    (void)st0;
+    T score = T(0);
+    {
+      T xd[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) xd[j] = sx(0, S_XT + j);
+      const T zero[5] = {T(0), T(0), T(0), T(0), T(0)};
+      for (int k = 0; k < N; ++k) {
+        const int ks = (k + c < N) ? (k + c) : (N - 1);
+        T u0 = m_min(m_max(rc(ks, R_U), P.dd_min), P.dd_max);
+        T u1 = m_min(rc(ks, R_U + 1), P.a_max);
+        if (k == 0) u1 = m_min(m_max(u1, a0_lo), a0_hi);
+        const Trig t = trig_of(xd[4] + sx(k, S_XR + 4), xd[2] + sx(k, S_XR + 2));
+        T roll[5];
+        defect(k, xd, zero, xd[3] + sx(k, S_XR + 3), t, u0, u1, roll);
+        score += P.R[0] * u0 * u0 + P.R[1] * u1 * u1;
+        if (k + 1 <= N - 1) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) score += P.Q[j] * roll[j] * roll[j];
+        }
+        const T de = roll[2] + sx(k + 1, S_XR + 2), vv = roll[3] + sx(k + 1, S_XR + 3);
+        const T viol = m_max(m_max(P.de_min - de, de - P.de_max), m_max(P.v_min - vv, vv - P.v_max));
+        score += T(1e4) * m_max(viol, T(0));
+#pragma unroll
+        for (int j = 0; j < 5; ++j) xd[j] = roll[j];
+      }
+    }
+    const T s_shift = w.shfl(score, 1), s_keep = w.shfl(score, 0);
+    const int pick = (s_shift < s_keep) ? 1 : 0;          // uniform
+    if (pick) {
+      // shift controls, slacks and multipliers one stage (R_U, R_V, R_S are adjacent: 16 words)
+      for (int k0 = 0; k0 < N; k0 += 32) {
+        const int k = k0 + lane;
+        T v[16];
+        if (k < N) {
+          const int ks = (k + 1 < N) ? k + 1 : N - 1;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = rc(ks, R_U + j);
+        }
+        w.sync();
+        if (k < N) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rc(k, R_U + j) = v[j];
+        }
+        w.sync();
+      }
+    }
+    // states of the chosen plan (every lane redundantly; lane k % 32 keeps stage k+1), controls clamped as rolled out
+    {
+      T xd[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) xd[j] = sx(0, S_XT + j);
+      const T zero[5] = {T(0), T(0), T(0), T(0), T(0)};
+      for (int k = 0; k < N; ++k) {
+        T u0 = m_min(m_max(rc(k, R_U), P.dd_min), P.dd_max);
+        T u1 = m_min(rc(k, R_U + 1), P.a_max);
+        if (k == 0) u1 = m_min(m_max(u1, a0_lo), a0_hi);
+        const Trig t = trig_of(xd[4] + sx(k, S_XR + 4), xd[2] + sx(k, S_XR + 2));
+        T roll[5];
+        defect(k, xd, zero, xd[3] + sx(k, S_XR + 3), t, u0, u1, roll);
+        if (lane == (k & 31)) {
+          rc(k, R_U) = u0; rc(k, R_U + 1) = u1;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) sx(k + 1, S_XT + j) = roll[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) xd[j] = roll[j];
+      }
+    }
+    w.sync();
+    return pick;
+  }
+  // Start of a solve whose slab already holds slacks / multipliers (previous MPC step, shifted; or an imported dual block):
+  // the iterate is pushed inside its bounds only by `warm_push`, every row keeps its multiplier -- brought to within
+  // [mu / kappa_warm, kappa_warm * mu] / s of the central path of the restart barrier parameter mu_warm -- and the barrier
+  // schedule restarts at mu_warm instead of mu0.  Every lane ends with the same (uniform) ProbState.
+  MPC_HD void init_warm(ProbState<T>& st) const {
+    const int N = P.N;
+    st.mu = P.mu_warm; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.nstall = 0; st.best = T(1e30); st.kkt = T(0);
+    st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
+    const T de0 = xa(0, 2), v0 = xa(0, 3);
+    const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
+    bool bad = false;
+    if (!(s0 < P.a_max) || !(s0 > -P.a_max)) bad = true;
+    const T amax0 = m_sqrt(m_max(P.a_max - s0, T(1e-12)));
+    st.a0_hi = m_min(amax0, P.a_max);
+    st.a0_lo = -amax0;
+    if (de0 < P.de_min || de0 > P.de_max || v0 < P.v_min || v0 > P.v_max) bad = true;
+    {
+      T sn, cs; m_sincos(xa(0, 4), &sn, &cs);
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, xa(0, 0), xa(0, 1), sn, cs, h, gx, gy, gp);
+        if (h < P.r_sum) bad = true;
+      }
+    }
+    if (bad) { st.status = ST_INFEASIBLE_X0; st.done = 1; }
+    const T kp = P.warm_push, mu = st.mu, kap = P.kappa_warm, ikap = T(1) / P.kappa_warm;
+    if (lane == 0) {
+      const Trig t = trig_of(xa(0, 4), xa(0, 2));
+      sx(0, S_TR) = t.sn; sx(0, S_TR + 1) = t.cs; sx(0, S_TR + 2) = t.tn;
+      sx(0, S_TRT) = t.sn; sx(0, S_TRT + 1) = t.cs; sx(0, S_TRT + 2) = t.tn;
+      for (int j = 0; j < 5; ++j) sx(0, S_XTT + j) = sx(0, S_XT + j);
+    }
+    auto recentre = [&](T nu, T s) { const T c = mu * m_rcp(s); return m_min(m_max(nu, c * ikap), c * kap); };
+    for (int k = lane; k < N; k += 32) {
+      const T pdd = m_min(kp, kp * (P.dd_max - P.dd_min));
+      T dd = m_min(m_max(rc(k, R_U), P.dd_min + pdd), P.dd_max - pdd);
+      const T ahi = (k == 0) ? st.a0_hi : P.a_max;
+      T a = rc(k, R_U + 1);
+      if (k == 0) {
+        const T pa = m_min(kp * m_max(T(1), ahi), kp * (ahi - st.a0_lo));
+        a = m_min(m_max(a, st.a0_lo + pa), ahi - pa);
+      } else {
+        a = m_min(a, ahi - kp * m_max(T(1), m_abs(ahi)));
+      }
+      rc(k, R_U) = dd; rc(k, R_U + 1) = a;
+      const T pde = m_min(kp * m_max(T(1), m_abs(P.de_max)), kp * (P.de_max - P.de_min));
+      const T pv = m_min(kp * m_max(T(1), m_abs(P.v_max)), kp * (P.v_max - P.v_min));
+      const T de = m_min(m_max(xa(k + 1, 2), P.de_min + pde), P.de_max - pde);
+      const T vv = m_min(m_max(xa(k + 1, 3), P.v_min + pv), P.v_max - pv);
+      sx(k + 1, S_XT + 2) = de - sx(k + 1, S_XR + 2);
+      sx(k + 1, S_XT + 3) = vv - sx(k + 1, S_XR + 3);
+      rc(k, R_V + V_DD_LO) = recentre(rc(k, R_V + V_DD_LO), dd - P.dd_min);
+      rc(k, R_V + V_DD_HI) = recentre(rc(k, R_V + V_DD_HI), P.dd_max - dd);
+      rc(k, R_V + V_A_HI) = recentre(rc(k, R_V + V_A_HI), ahi - a);
+      {                                                                               // exists at stage 0 only
+        const T old = rc(k, R_V + V_A_LO);
+        rc(k, R_V + V_A_LO) = (k == 0) ? ((old > T(0)) ? recentre(old, a - st.a0_lo) : mu * m_rcp(a - st.a0_lo)) : T(0);
+      }
+      rc(k, R_V + V_DE_LO) = recentre(rc(k, R_V + V_DE_LO), de - P.de_min);
+      rc(k, R_V + V_DE_HI) = recentre(rc(k, R_V + V_DE_HI), P.de_max - de);
+      rc(k, R_V + V_V_LO) = recentre(rc(k, R_V + V_V_LO), vv - P.v_min);
+      rc(k, R_V + V_V_HI) = recentre(rc(k, R_V + V_V_HI), P.v_max - vv);
+      const Trig t = trig_of(xa(k + 1, 4), xa(k + 1, 2));
+      sx(k + 1, S_TR) = t.sn; sx(k + 1, S_TR + 1) = t.cs; sx(k + 1, S_TR + 2) = t.tn;
+      for (int j = 0; j < 3; ++j) {
+        T h, gx, gy, gp; obst(j, xa(k + 1, 0), xa(k + 1, 1), t.sn, t.cs, h, gx, gy, gp);
+        const T c = h - P.r_sum;
+        const T s = m_max(m_max(c, rc(k, R_S + j)), kp * m_max(T(1), P.r_sum));
+        rc(k, R_S + j) = s;
+        rc(k, R_V + V_OB0 + j) = recentre(rc(k, R_V + V_OB0 + j), s);
       }
       for (int j = 0; j < 5; ++j) rc(k, R_DX + j) = T(0);
       rc(k, R_DU) = T(0); rc(k, R_DU + 1) = T(0);

@@ -167,8 +167,7 @@ class B200Optimizer(_Base):
         for j in range(3):
             cfg.obstacle[2 * j] = float(self.obstacle_circles_centers_tuple[j][0])
             cfg.obstacle[2 * j + 1] = float(self.obstacle_circles_centers_tuple[j][1])
-        for k, v in solver_opts.items():
-            setattr(cfg, k, v)
+        _capi.set_options(cfg, solver_opts)            # raises on a name that is not a field of mpcb200_config
         self.cfg = cfg
         self.N = N
         with torch.cuda.device(self.device):
@@ -192,22 +191,31 @@ class B200Optimizer(_Base):
         return self._path_d
 
     # ------------------------------------------------------------------ batched API (device tensors in / out)
-    def solve_batch(self, xref, X_init=None, U_init=None):
+    def solve_batch(self, xref, X_init=None, U_init=None, out=None):
         """One NLP solve per row (replaces optimizer.py:605-607).  xref [B,N+1,5] (row 0 = current state).
-        Returns (U*[B,N,2], X*[B,N+1,5], status[B] int32, iters[B] int32) as CUDA tensors (float64)."""
+        Returns (U*[B,N,2], X*[B,N+1,5], status[B] int32, iters[B] int32) as CUDA tensors (float64).
+        out=(U, X, status, iters): contiguous CUDA tensors (views of larger ones are fine) that receive the results."""
         t = self.torch
         xref = self._dev(xref)
         B = xref.shape[0]
         assert xref.shape[1:] == (self.N + 1, 5), xref.shape
         cold = X_init is None and U_init is None
-        if cold:
-            X = t.empty(B, self.N + 1, 5, dtype=t.float64, device=self.device)
-            U = t.empty(B, self.N, 2, dtype=t.float64, device=self.device)
+        if out is not None:
+            U, X, status, iters = out
+            assert U.is_contiguous() and X.is_contiguous() and U.shape == (B, self.N, 2) and X.shape == (B, self.N + 1, 5)
+            assert U.dtype == t.float64 and X.dtype == t.float64 and status.dtype == t.int32 and iters.dtype == t.int32
+            if not cold:
+                X.copy_(xref[:, :1, :].expand(B, self.N + 1, 5) if X_init is None else self._dev(X_init))
+                U.copy_(t.zeros_like(U) if U_init is None else self._dev(U_init))
         else:
-            X = (xref[:, :1, :].expand(B, self.N + 1, 5).contiguous() if X_init is None else self._dev(X_init).clone())
-            U = (t.zeros(B, self.N, 2, dtype=t.float64, device=self.device) if U_init is None else self._dev(U_init).clone())
-        status = t.empty(B, dtype=t.int32, device=self.device)
-        iters = t.empty(B, dtype=t.int32, device=self.device)
+            if cold:
+                X = t.empty(B, self.N + 1, 5, dtype=t.float64, device=self.device)
+                U = t.empty(B, self.N, 2, dtype=t.float64, device=self.device)
+            else:
+                X = (xref[:, :1, :].expand(B, self.N + 1, 5).contiguous() if X_init is None else self._dev(X_init).clone())
+                U = (t.zeros(B, self.N, 2, dtype=t.float64, device=self.device) if U_init is None else self._dev(U_init).clone())
+            status = t.empty(B, dtype=t.int32, device=self.device)
+            iters = t.empty(B, dtype=t.int32, device=self.device)
         h = self.handle
         fn = h.lib.mpcb200_solve_cold if cold else h.lib.mpcb200_solve
         h.check(fn(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), B, self._stream()))
@@ -311,43 +319,59 @@ class B200Optimizer(_Base):
         return traj.cpu().numpy(), ctrl.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
 
     # ------------------------------------------------------------------ the reference contract
-    def optimize(self):
+    def optimize(self, on_device=None):
         """CasadiOptimizer.optimize() (optimizer.py:562-643): returns (traj_s[T,5], u[T,2], t_v[T]).
 
-        The loop shape is the reference's (solve -> first control -> plant step + shift -> next window); solve time per
-        step is measured like the reference does (wall clock around the solve, optimizer.py:603-608).  `noised` is
-        honoured with the reference's own noise law when N == 10 (optimizer.py:611-615, quirk Q9)."""
+        Noise-free runs (`configuration.noised` false) execute the whole receding-horizon loop on the device in ONE launch
+        (`mpcb200_closed_loop` = `optimize_batch` with B = 1); `t_v` then holds the measured loop time divided evenly over the
+        T steps (the device loop has no per-step host clock).  With `noised` (or `on_device=False`) the loop runs step by
+        step from the host in the reference's own shape -- solve -> first control (+ noise) -> plant step + shift -> next
+        window -- with the solve time of each step measured like the reference does (wall clock around the solve,
+        optimizer.py:603-608).  `noised` uses the reference's noise law and needs N == 10 (optimizer.py:611-615, quirk Q9)."""
         t = self.torch
         N, T = self.N, int(self.iter_length)
         init_state = np.array([self.init_position[0], self.init_position[1], 0.0, self.init_velocity,
                                self.init_orientation], float)
+        noised = bool(getattr(self.configuration, "noised", False))
+        if on_device is None:
+            on_device = not noised
+        if on_device:
+            if noised:
+                raise ValueError("the device loop is noise-free; use on_device=False with configuration.noised")
+            t.cuda.synchronize(self.device)
+            t_ = time.time()
+            traj, ctrl, status, iters = self.optimize_batch(init_state[None, :])
+            dt_loop = time.time() - t_
+            self.last_status, self.last_iters = status[0], iters[0]
+            return traj[0], ctrl[0], np.full(T, dt_loop / T)
         x = self._dev(init_state[None, :])
         xref = x[:, None, :].expand(1, N + 1, 5).contiguous()      # Q4: first parameter block = x0 tiled
         X = xref.clone()
         U = t.zeros(1, N, 2, dtype=t.float64, device=self.device)
-        traj, u_c, t_v = [], [], []
-        noised = bool(getattr(self.configuration, "noised", False))
+        traj, u_c, t_v, sts, its = [], [], [], [], []
         for i in range(T):
             t.cuda.synchronize(self.device)
             t_ = time.time()
             U, X, status, iters = self.solve_batch(xref, X, U)
             t.cuda.synchronize(self.device)
             t_v.append(time.time() - t_)
+            sts.append(status); its.append(iters)
             if noised:
                 if N != 10:
                     raise ValueError("noised=True draws 20 = 2*10 samples in the reference (optimizer.py:613); N must be 10")
                 sigma = 0.1 if getattr(self.configuration, "use_case", "lane_following") == "lane_following" else 0.05
                 noise = np.random.normal(0, sigma, 20).reshape(2, N).T
                 U = U + self._dev(noise[None])
-            u_applied = self.plant_step_shift(x, U, X)
-            u_c.append(u_applied[0].cpu().numpy())
-            traj.append(x[0].cpu().numpy().copy())
+            u_c.append(self.plant_step_shift(x, U, X))
+            traj.append(x.clone())
             xref = self.build_ref_window(i, x)
-        traj_s = np.array(traj)
+        # one device -> host transfer for the whole run
+        traj_s = t.cat(traj, dim=0).cpu().numpy()
+        u_out = t.cat(u_c, dim=0).cpu().numpy()
+        self.last_status, self.last_iters = t.cat(sts).cpu().numpy(), t.cat(its).cpu().numpy()
         traj_s = np.insert(traj_s, 0, init_state, axis=0)
         traj_s = np.delete(traj_s, -1, axis=0)
-        return traj_s, np.array(u_c), np.array(t_v)
-
+        return traj_s, u_out, np.array(t_v)
 
     def save_results(self, save_path, states, controls, solve_time):
         """Writes `planned states.txt`, `control inputs.txt`, `solve time.txt`, `deviation.txt`, `RMSD.txt` in the format

@@ -58,3 +58,43 @@ def solve_sharded(solve_fn, xref, X_init, U_init, gather=True):
     if not gather:
         return U, X, status, iters
     return (gather_solutions(U, B), gather_solutions(X, B), gather_solutions(status, B), gather_solutions(iters, B))
+
+
+def solve_sharded_nccl(opt, xref_global, B, N, src=0):
+    """The multi-GPU data path of the batched solve: rank `src` owns the global parameter block
+    `xref_global` [B,N+1,5] (a CUDA tensor there, None elsewhere).  Shards go out and solutions come back as point-to-point
+    NCCL transfers batched into ONE group each (`batch_isend_irecv`: a single NCCL launch over NVLink, received straight
+    into slices of the global result tensors -- no padding, no staging copies); rank `src` solves its own shard in place
+    while its sends are in flight.  No collective inside the solve.  Returns (U [B,N,2], X [B,N+1,5], status [B], iters [B])
+    on `src`, None elsewhere.  Everything is stream-ordered on the current CUDA stream (no host synchronisation)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_range(B, rank, world)
+    dev, f64 = opt.device, torch.float64
+    if rank == src:
+        U = torch.empty(B, N, 2, dtype=f64, device=dev)
+        X = torch.empty(B, N + 1, 5, dtype=f64, device=dev)
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev)
+        spans = [(r,) + shard_range(B, r, world) for r in range(world) if r != src]
+        sends = [dist.P2POp(dist.isend, xref_global[l:h], r) for r, l, h in spans if h > l]
+        reqs = dist.batch_isend_irecv(sends) if sends else []
+        opt.solve_batch(xref_global[lo:hi], out=(U[lo:hi], X[lo:hi], st[lo:hi], it[lo:hi]))
+        for q in reqs:
+            q.wait()
+        recvs = []
+        for r, l, h in spans:
+            if h > l:
+                recvs += [dist.P2POp(dist.irecv, t[l:h], r) for t in (U, X, st, it)]
+        for q in (dist.batch_isend_irecv(recvs) if recvs else []):
+            q.wait()
+        return U, X, st, it
+    if hi > lo:
+        xr = torch.empty(hi - lo, N + 1, 5, dtype=f64, device=dev)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, xr, src)]):
+            q.wait()
+        Ul, Xl, stl, itl = opt.solve_batch(xr)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, src) for t in (Ul, Xl, stl, itl)]):
+            q.wait()
+    return None

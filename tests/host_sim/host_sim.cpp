@@ -8,6 +8,7 @@
 #include <cmath>
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/config_params.h"
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/warp_core.cuh"
+#include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/loop_core.cuh"
 
 using namespace mpcb200;
 
@@ -61,7 +62,52 @@ static void run(const mpcb200_config& cfg, const double* xref, double* Xio, doub
   }
 }
 
+// ---- the closed loop (loop_core.cuh: the body of mpc_warp_closed_loop_kernel) for one ego per emulated warp
+template <typename T>
+struct LoopJob {
+  const mpcb200_config* cfg;
+  ParamsT<T> P;
+  T* slab;
+  LoopData d;
+  int b;
+  double* stg;
+  HostWarp* hw;
+};
+template <typename T>
+static void loop_lane_body(int lane, void* arg) {
+  LoopJob<T>& J = *(LoopJob<T>*)arg;
+  WarpCtx w(J.hw, lane);
+  T obs[6];
+  WarpSolver<T> S(J.P, SlabRef<T>{J.slab, 0}, obs, w);
+  const int nx = 5 * (J.P.N + 1);
+  closed_loop_ego<T, HESS_RUNTIME>(S, J.d, J.b, J.stg, J.stg + nx, J.stg + 2 * nx, obs, J.cfg->max_iter);
+}
+template <typename T>
+static void run_loop(const mpcb200_config& cfg, const LoopData& d) {
+  const int N = cfg.N;
+  WLayout L(N);
+  std::vector<T> buf(L.words + REC_STRIDE + 4);
+  std::vector<double> stg(12 * N + 10);
+  HostWarp hw;
+  for (int b = 0; b < d.B; ++b) {
+    LoopJob<T> J;
+    J.cfg = &cfg; J.P = params_from_config<T>(cfg); J.slab = buf.data(); J.d = d; J.b = b; J.stg = stg.data(); J.hw = &hw;
+    for (auto& v : buf) v = T(NAN);
+    hw.run(&loop_lane_body<T>, &J);
+  }
+}
+
 extern "C" {
+int hostsim_closed_loop(const mpcb200_config* cfg, int iter_length, const double* path, const double* orient, double vdes, const double* x0,
+                        double* traj, double* ctrl, int* status, int* iters, int B) {
+  LoopData d;
+  for (int i = 0; i < 6; ++i) d.obstacle[i] = cfg->obstacle[i];
+  d.path = path; d.orient = orient; d.x0 = x0; d.traj = traj; d.ctrl = ctrl; d.status = status; d.iters = iters;
+  d.desired_velocity = vdes; d.l_wb = cfg->l_wb; d.dt = cfg->dt; d.B = B; d.Tlen = iter_length; d.warm_duals = cfg->warm_duals;
+  if (cfg->precision == MPCB200_F64) run_loop<double>(*cfg, d); else run_loop<float>(*cfg, d);
+  return 0;
+}
+void hostsim_trace_step(int i) { mpc_trace_step = i; }
 void hostsim_default_config(mpcb200_config* c, int N, int precision) { default_config(c, N, precision); }
 int hostsim_solve(const mpcb200_config* cfg, const double* xref, double* X, double* U, int* status, int* iters,
                   double* kkt, int B, int trace) {

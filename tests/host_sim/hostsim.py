@@ -19,7 +19,9 @@ class Config(C.Structure):
                  ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_factor", C.c_double), ("tol_step", C.c_double),
                  ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double), ("mu_min_alpha", C.c_double), ("mu_up_alpha", C.c_double), ("mu_up_factor", C.c_double), ("mu_max", C.c_double), ("mu_factor_full", C.c_double),
                  ("kappa_sigma", C.c_double), ("screen_inv_curv", C.c_double), ("trust_step", C.c_double), ("acc_factor", C.c_double),
-                 ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32)])
+                 ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32),
+                 ("mu_warm", C.c_double), ("warm_push", C.c_double), ("kappa_warm", C.c_double),
+                 ("warm_duals", C.c_int32), ("warps_per_cta", C.c_int32), ("host_route", C.c_int32), ("host_chunks", C.c_int32)])
 
 
 _lib = None
@@ -31,7 +33,7 @@ def lib():
         so = os.path.join(HERE, "libhostsim.so")
         src = os.path.join(HERE, "host_sim.cpp")
         csrc = os.path.join(HERE, "..", "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "loop_core.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
         if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMPC_DIAG", "-shared", "-fPIC", "-o", so, src], cwd=HERE)
         _lib = C.CDLL(so)
@@ -55,3 +57,17 @@ def solve(cfg, xref, X, U, trace=0):
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     lib().hostsim_solve(C.byref(cfg), p(xref), p(X), p(U), p(st), p(it), p(kkt), B, trace)
     return X, U, st, it, kkt
+
+
+def closed_loop(cfg, sc, x0):
+    """The device closed-loop body (csrc/loop_core.cuh) on the emulator: x0 [B,5] -> traj [B,T,5], ctrl [B,T,2], status, iters [B,T]."""
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), np.float64)
+    B, T = x0.shape[0], int(sc.iter_length)
+    path = np.ascontiguousarray(np.asarray(sc.reference_path, float)[:, :2])
+    orient = np.ascontiguousarray(np.asarray(sc.orientation, float))
+    traj = np.zeros((B, T, 5)); ctrl = np.zeros((B, T, 2))
+    st = np.zeros((B, T), np.int32); it = np.zeros((B, T), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hostsim_closed_loop.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5 + [C.c_int]
+    lib().hostsim_closed_loop(C.byref(cfg), T, p(path), p(orient), float(sc.desired_velocity), p(x0), p(traj), p(ctrl), p(st), p(it), B)
+    return traj, ctrl, st, it

@@ -25,15 +25,28 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_capi.EXPORTS.keys()) == names     # the ctypes table covers the header, nothing more
 
 
-def test_config_struct_matches_header_layout():
+def test_config_struct_matches_header_layout(tmp_path):
+    """The ctypes mirror of mpcb200_config against the C compiler's view of include/mpcb200.h: size and every field offset."""
+    import subprocess
     from mpc_b200 import _capi
     cfg = _capi.default_config(30, _capi.F32)
-    assert cfg.abi_version == _capi.ABI_VERSION == 3 and cfg.N == 30
-    assert C.sizeof(_capi.Config) == 8 * 4 + 8 * (3 + 5 + 2 + 7 + 2 + 6 + 7 + 9) + 4 * 4
+    assert cfg.abi_version == _capi.ABI_VERSION == 4 and cfg.N == 30
+    names = [n for n, _ in _capi.Config._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "mpcb200.h"\nint main(void){printf("%zu\\n", sizeof(mpcb200_config));' + \
+           "".join('printf("%%zu\\n", offsetof(mpcb200_config, %s));' % n for n in names) + "return 0;}"
+    src = tmp_path / "layout.c"
+    src.write_text(prog)
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "layout"), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(tmp_path / "layout")]).split()]
+    assert out[0] == C.sizeof(_capi.Config)
+    assert out[1:] == [getattr(_capi.Config, n).offset for n in names]
     assert abs(cfg.l_wb - 2.5789128) < 1e-12 and cfg.l_fric == 2.578
     assert (cfg.deltav_min, cfg.deltav_max, cfg.a_max, cfg.v_min, cfg.v_max) == (-0.4, 0.4, 11.5, 0.0, 50.8)
     c64 = _capi.default_config(50, _capi.F64)
     assert c64.mu_min < cfg.mu_min and c64.tol_step < cfg.tol_step
+    # the host emulator's mirror (test tooling) must be the same struct
+    import hostsim
+    assert [(n, t) for n, t in hostsim.Config._fields_] == [(n, t) for n, t in _capi.Config._fields_]
 
 
 def test_no_cpu_fallback_create_fails_loudly_without_gpu():

@@ -38,7 +38,7 @@ def test_solve_matches_oracle_golden(key, name, N, precision, hessian):
     assert (st == 1).all(), st
     assert np.abs(U - g[key + "_U"]).max() < TOL[precision]
     assert np.abs(X - g[key + "_X"]).max() < TOL[precision]
-    assert opt.handle.launch_count == 1          # one fused launch ran every SQP iteration
+    assert opt.handle.launch_count == (2 if precision == "f32" else 1)          # one fused launch ran every SQP iteration (+ the refinement pass of a float32 handle)
 
 
 def test_step0_known_answer_both_weight_sets():
@@ -83,7 +83,7 @@ def test_stepwise_launches_equal_fused_launch():
     U1, X1, st1, it1 = _np(*opt.solve_batch(xref, X0, U0))
     n0 = opt.handle.launch_count
     U2, X2, st2, it2 = _np(*opt.solve_batch_stepwise(xref, X0, U0, n_iter=int(it1.max()) + 2))
-    assert opt.handle.launch_count - n0 == int(it1.max()) + 4       # begin + n_iter + end
+    assert opt.handle.launch_count - n0 == int(it1.max()) + 4       # begin + n_iter + end (the stepwise mode has no refinement pass)
     assert np.array_equal(st1, st2) and np.array_equal(it1, it2)
     assert np.array_equal(U1, U2) and np.array_equal(X1, X2)          # bit-identical: same arithmetic, slab round-trips via TMA
 
@@ -133,7 +133,7 @@ def test_collision_avoidance_kkt_points_config3_sample():
     # fp32 arithmetic: the cold-start path to a minimum is chaotic (blocked steps around the obstacle), so a few
     # instances end in a different basin than the float64 run; every fp32 point must still be a minimum of the
     # reference NLP (oracle warm-started there stays within the fp32 tolerance) and most coincide with float64
-    sc, opt32 = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300)
+    sc, opt32 = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300, refine_f64=0)      # float32 pass alone
     U32, X32, st32, _ = _np(*opt32.solve_batch(xref, X0, U0))
     ok = st32 == 1
     assert np.isin(st32, (1, 3)).all(), st32          # 3 = stalled at the fp32 rounding floor (stiff active obstacle row)
@@ -272,15 +272,15 @@ def test_float64_refinement_pass_converges_the_stalled_collision_avoidance_insta
     from oracle import nlp, ipm
     N, B = 30, 256
     _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_CA", B, N, 20261018)
-    sc, opt = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300)
+    sc, opt = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300, refine_f64=0)
     U, X, st, it = _np(*opt.solve_batch(xref))
-    sc, optr = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300, refine_f64=1)
+    sc, optr = _opt("ZAM_Over-1_1_CA", N, "f32", max_batch=B, max_iter=300)                    # refine_f64 = 1 is the float32 default
     Ur, Xr, str_, itr = _np(*optr.solve_batch(xref))
     assert optr.handle.launch_count == 2
     same = st == 1
     assert same.any() and (~same).any()                                     # the sample has stalled instances
     assert np.array_equal(U[same], Ur[same]) and np.array_equal(X[same], Xr[same]) and np.array_equal(it[same], itr[same])
-    assert (str_ == 1).mean() > 0.99 and (itr[~same] > it[~same]).all()
+    assert (str_ == 1).all() and (itr[~same] > it[~same]).all()
     for b in [int(i) for i in np.where(~same & (str_ == 1))[0][:3]]:
         d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
         w = nlp.pack(Ur[b], Xr[b])
@@ -320,9 +320,9 @@ def test_long_horizon_and_small_horizon_edges():
         opt.solve_batch(xref)                                     # B > max_batch is an API error, not a crash
 
 
-def test_host_path_zero_copy_route_is_bit_identical_to_the_staged_route_and_the_device_path(monkeypatch):
+def test_host_path_zero_copy_route_is_bit_identical_to_the_staged_route_and_the_device_path():
     """mpcb200_solve_host with pinned buffers = ONE launch whose TMA bulk copies read / write host memory directly;
-    with pageable buffers (or MPCB200_HOST_STAGED=1) = staged copy pipeline.  Same arithmetic either way."""
+    with pageable buffers (or cfg.host_route = 1) = staged copy pipeline.  Same arithmetic either way."""
     import torch
     import mpc_b200
     N, B = 30, 257                                                    # odd: the last CTA tile is ragged (plain-loop I/O)
@@ -333,7 +333,7 @@ def test_host_path_zero_copy_route_is_bit_identical_to_the_staged_route_and_the_
     hx, hX, hU = pin(xref), pin(np.full_like(X0, np.nan)), pin(np.full_like(U0, np.nan))
     n0 = opt.handle.launch_count
     Uz, Xz, stz, itz = opt.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
-    assert opt.handle.launch_count - n0 == 1                          # one launch, no chunking
+    assert opt.handle.launch_count - n0 == 2                          # float32 pass + (empty) float64 refinement pass, no chunking
     assert np.array_equal(Uz, Ua) and np.array_equal(Xz, Xa) and np.array_equal(stz, sta) and np.array_equal(itz, ita)
     # warm start through pinned buffers, separate in / out arrays: one further iteration or so, same as the device path
     hXi, hUi = pin(Xa), pin(Ua)
@@ -346,12 +346,11 @@ def test_host_path_zero_copy_route_is_bit_identical_to_the_staged_route_and_the_
     Ui, Xi, sti, iti = opt.solve_batch_host(hx.numpy(), hXi.numpy(), hUi.numpy(), inplace=True)
     assert np.array_equal(Ui, Ub) and np.array_equal(Xi, Xb)
     # staged route forced / pageable buffers
-    monkeypatch.setenv("MPCB200_HOST_STAGED", "1")
-    n0 = opt.handle.launch_count
-    Us, Xs, sts, its = opt.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
-    assert opt.handle.launch_count - n0 >= 1
+    sc, opt_st = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=512, host_route=1, host_chunks=3)
+    n0 = opt_st.handle.launch_count
+    Us, Xs, sts, its = opt_st.solve_batch_host(hx.numpy(), out=(hX.numpy(), hU.numpy()))
+    assert opt_st.handle.launch_count - n0 >= 3
     assert np.array_equal(Us, Ua) and np.array_equal(Xs, Xa) and np.array_equal(sts, sta)
-    monkeypatch.delenv("MPCB200_HOST_STAGED")
     Up, Xp, stp, itp = opt.solve_batch_host(xref)                     # pageable numpy arrays -> staged
     assert np.array_equal(Up, Ua) and np.array_equal(Xp, Xa) and np.array_equal(itp, ita)
 
@@ -439,3 +438,145 @@ def test_full_config2_batch_against_the_oracle_every_instance():
     U6 = opt6.solve_batch(xref)[0].cpu().numpy()
     d6 = max(np.abs(nlp.split(w_o, N)[0] - U6[b]).max() for b, (_, _, w_o) in enumerate(res))
     assert d6 > dU
+
+
+def test_misaligned_slices_and_mixed_handles():
+    """(i) a problem row is 40(N+1) bytes = 8 (mod 16) for even N, so xref[1:] (and every odd shard start) is not
+    16-byte aligned -- the per-warp TMA copy moves the aligned interior and plain loads the 8-byte edges; (ii) the dynamic
+    shared-memory opt-in is a property of the kernel, not of the handle: a later, smaller handle must not break an earlier one."""
+    import torch
+    import mpc_b200
+    N, B = 30, 67
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=128)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 5)
+    Ua, Xa, sta, ita = _np(*opt.solve_batch(xref))
+    d = opt._dev(xref)
+    for lo in (1, 2, 33):
+        Ub, Xb, stb, itb = _np(*opt.solve_batch(d[lo:]))                     # view, no copy: data_ptr is 8 (mod 16) for odd lo
+        assert d[lo:].data_ptr() % 16 == (8 * (lo % 2))
+        assert np.array_equal(Ub, Ua[lo:]) and np.array_equal(Xb, Xa[lo:]) and np.array_equal(stb, sta[lo:])
+    # warm start + outputs in views with odd offsets
+    Uo = torch.full((B + 1, N, 2), float("nan"), dtype=torch.float64, device="cuda")
+    Xo = torch.full((B + 1, N + 1, 5), float("nan"), dtype=torch.float64, device="cuda")
+    so = torch.zeros(B + 1, dtype=torch.int32, device="cuda"); io = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
+    opt.solve_batch(d, X0, U0, out=(Uo[1:], Xo[1:], so[1:], io[1:]))
+    assert np.array_equal(Uo[1:].cpu().numpy(), Ua) and np.array_equal(Xo[1:].cpu().numpy(), Xa) and torch.isnan(Uo[0]).all()
+    # pinned host slice through the zero-copy route
+    hx, hX, hU = opt.alloc_host_buffers(B + 1)
+    hx[1:] = xref
+    Uh, Xh, sth, _ = opt.solve_batch_host(hx[1:], out=(hX[1:], hU[1:]))
+    assert np.array_equal(Uh, Ua) and np.array_equal(Xh, Xa)
+    # mixed handles: float64 N = 30 needs > 48 KB of dynamic shared memory per CTA; create smaller handles afterwards
+    sc, big = _opt("ZAM_Over-1_1_LF", 30, "f64", max_batch=128)
+    U1 = big.solve_batch(xref)[0].cpu().numpy()
+    sc, small = _opt("ZAM_Over-1_1_LF", 4, "f64", max_batch=8)
+    sc, small32 = _opt("ZAM_Over-1_1_LF", 10, "f32", max_batch=8)
+    U2 = big.solve_batch(xref)[0].cpu().numpy()
+    assert np.array_equal(U1, U2) and np.abs(U1 - Ua).max() < 1e-3
+    with pytest.raises(Exception):
+        _opt("ZAM_Over-1_1_LF", 30, "f32", max_batch=8, no_such_option=1)      # unknown option names are an error, not ignored
+
+
+def test_large_batch_runs_on_the_persistent_grid_with_dynamic_work_claiming():
+    """B far above the resident warps: the grid is capped at the resident CTAs and warps claim further problems from the
+    device counter.  Results must be those of the same problems solved in small batches (order of execution is irrelevant),
+    twice in a row (the counters reset themselves)."""
+    import mpc_b200
+    N, B = 30, 6000
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=B)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 99)
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert (st == 1).all()
+    sc, small = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=512)
+    for lo in (0, 2500, 5488):
+        Us, Xs, sts, its = _np(*small.solve_batch(xref[lo:lo + 512]))
+        assert np.array_equal(Us, U[lo:lo + 512]) and np.array_equal(Xs, X[lo:lo + 512]) and np.array_equal(its, it[lo:lo + 512])
+    U2, X2, st2, it2 = _np(*opt.solve_batch(xref))
+    assert np.array_equal(U, U2) and np.array_equal(it, it2)
+    # closed loop on the persistent grid as well
+    x0b = mpc_b200.perturbed_initial_states(sc, 4000, 3)
+    sc10, opt10 = _opt("ZAM_Over-1_1_LF", 10, "f32", max_batch=4096)
+    tr, ct, stl, itl = opt10.optimize_batch(x0b)
+    tr2, ct2, _, _ = opt10.optimize_batch(x0b[3000:3064])
+    assert np.array_equal(tr[3000:3064], tr2) and np.array_equal(ct[3000:3064], ct2) and (stl == 1).mean() > 0.99
+
+
+def test_full_config3_batch_every_instance_is_a_local_optimum_by_default():
+    """BASELINE configs[2] at full size, DEFAULT options (float32 arithmetic + the float64 refinement pass of whatever the
+    float32 pass did not converge): all 4096 instances end with status 1 and keep the 3.3 m clearance.  The NLP is multi-modal
+    from a cold start (pass left / right of the obstacle), so parity is stated per instance as: the float64 oracle warm-started
+    AT the GPU point converges and stays within the stated tolerance 1e-3 (i.e. the GPU point is that close to a local optimum
+    of the reference NLP).  Every instance, oracle on all host cores."""
+    import multiprocessing as mp
+    import sys
+    import mpc_b200
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    name, N, B = "ZAM_Over-1_1_CA", 30, 4096
+    sc, opt = _opt(name, N, "f32", max_batch=B, max_iter=300)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 20261018)
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert (st == 1).all(), np.unique(st, return_counts=True)
+    cores = min(os.cpu_count() or 1, 32)
+    with mp.get_context("fork").Pool(cores, initializer=_one_blas_thread) as pool:
+        res = pool.map(bench._warm_one, [(name, N, xref[b], X[b], U[b]) for b in range(B)], chunksize=8)
+    sto = np.array([r[0] for r in res]); dw = np.array([r[1] for r in res]); clr = np.array([r[2] for r in res])
+    assert (sto == 1).mean() > 0.995                    # the oracle's own IPM fails on a handful of starts
+    assert dw[sto == 1].max() < 1e-3, (dw[sto == 1].max(), int((dw[sto == 1] > 1e-3).sum()))
+    assert np.median(dw[sto == 1]) < 1e-4
+    assert clr.min() > -1e-5
+
+
+def test_config4_lanker_n50_against_the_oracle_on_1024_instances():
+    """BASELINE configs[3] (USA_Lanker, N = 50, B = 8192): every instance converges; 1024 evenly spaced ones are compared with
+    the float64 oracle instance by instance (stated tolerance 1e-3)."""
+    import multiprocessing as mp
+    import sys
+    import mpc_b200
+    from oracle import nlp
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    name, N, B = "USA_Lanker-2_18_T-1_LF", 50, 8192
+    sc, opt = _opt(name, N, "f32", max_batch=B, max_iter=300)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 20261019)
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert (st == 1).all(), np.unique(st, return_counts=True)
+    idx = np.linspace(0, B - 1, 1024).astype(int)
+    cores = min(os.cpu_count() or 1, 32)
+    with mp.get_context("fork").Pool(cores, initializer=_one_blas_thread) as pool:
+        res = pool.map(bench._oracle_one, [(name, N, xref[b], X0[b], U0[b]) for b in idx], chunksize=4)
+    n_cmp = 0
+    for b, (st_o, _, w_o) in zip(idx, res):
+        if st_o != 1:
+            continue                                   # the oracle's own IPM is less robust than the device solver
+        Uo, Xo = nlp.split(w_o, N)
+        assert np.abs(Uo - U[b]).max() < 1e-3 and np.abs(Xo - X[b]).max() < 1e-3, b
+        n_cmp += 1
+    assert n_cmp >= 800                              # the oracle IPM itself fails on ~15 % of the Lanker starts
+
+
+@pytest.mark.parametrize("name", ["ZAM_Over-1_1_LFfile", "USA_Peach-2_1_T-1", "ZAM_Tutorial-1_2_T-1", "ZAM_Tutorial_Urban-3_2"])
+def test_config5_scenarios_512_instances_each_against_the_oracle(name):
+    """BASELINE configs[4]: 512 instances per scenario, each compared with the float64 oracle (tolerance 1e-3)."""
+    import multiprocessing as mp
+    import sys
+    import mpc_b200
+    from oracle import nlp
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    N, B = 30, 512
+    sc, opt = _opt(name, N, "f32", max_batch=B, max_iter=300)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 20261020)
+    U, X, st, it = _np(*opt.solve_batch(xref))
+    assert (st == 1).all(), np.unique(st, return_counts=True)
+    cores = min(os.cpu_count() or 1, 32)
+    with mp.get_context("fork").Pool(cores, initializer=_one_blas_thread) as pool:
+        res = pool.map(bench._oracle_one, [(name, N, xref[b], X0[b], U0[b]) for b in range(B)], chunksize=4)
+    n_cmp = 0
+    for b, (st_o, _, w_o) in enumerate(res):
+        if st_o != 1:
+            continue
+        Uo, Xo = nlp.split(w_o, N)
+        assert np.abs(Uo - U[b]).max() < 1e-3 and np.abs(Xo - X[b]).max() < 1e-3, b
+        n_cmp += 1
+    assert n_cmp >= 0.9 * B
