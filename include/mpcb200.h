@@ -77,6 +77,7 @@ typedef struct mpcb200_config {
   double mu_warm;                  /* dual warm start: barrier parameter a warm-started solve restarts at (instead of mu0) */
   double warm_push;                /* dual warm start: relative interior push of the warm primal point (instead of bound_push) */
   double kappa_warm;               /* dual warm start: carried multipliers are kept within [mu_warm/(kappa s), kappa mu_warm/s] */
+  double stiff_slack;              /* float32: an acceptable-level exit while a live obstacle row has a slack below this is reported as status 3 (refined in float64 when refine_f64 is set) */
   int32_t warm_duals;              /* mpcb200_closed_loop: 1 = carry slacks / multipliers across MPC steps (shifted one stage), 0 = IPOPT-like restart every step */
   int32_t warps_per_cta;           /* problems (= warps) per CTA: 0 = library default, else 1 | 2 | 4 */
   int32_t host_route;              /* mpcb200_solve_host: 0 = zero-copy when every buffer is pinned, else staged; 1 = always staged */
@@ -138,6 +139,20 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
  *     pipelined in chunks over internal streams.  Same arithmetic, bit-identical results either way. */
 int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U,
                        double* h_X_out, double* h_U_out, int32_t* h_status, int32_t* h_iters, int32_t B);
+
+/* Stage functions of the reference's FORCESPRO formulation and their first derivatives -- the linearisation one SQP stage on that
+ * formulation needs (ForcesproOptimizer: RK4 dynamics optimizer.py:90-98, friction circle + nine squared circle distances
+ * :119-155, stage / terminal least-squares objective :163-195).  Replaces the generated model callbacks the FORCESPRO solver
+ * calls per stage: FORCESNLPsolver_{dynamics,ddynamics,inequalities,dinequalities,objective,dobjective}_0 and _1
+ * (test/FORCESNLPsolver/FORCESNLPsolver_model.c:74-1756, dispatched by FORCESNLPsolver_interface.c:84-191).
+ *   d_z [n][7]  stage variables [deltaDot, aLong, xPos, yPos, delta, v, psi]
+ *   d_p [n][10] stage parameters [path_x, path_y, v_des, psi_ref, obstacle centre / front / rear circle x, y]
+ *   d_out [n][136] = c(5) | dc/dz (5x7 row-major) | h(10) | dh/dz (10x7) | f | df/dz(7) | f_terminal | df_terminal/dz(7)
+ * Stage weights Q, R, dt, wheelbases and the ego circle offset come from the handle's config; `weights_terminal` [5] (host
+ * pointer) are the weight_*_terminate values.  float64 arithmetic.  The SQP solver on this formulation is not built yet (it
+ * needs the Riccati sweep generalised to a non-constant input matrix and a state-input cross term); this is its linearisation. */
+int mpcb200_forces_stage_eval(mpcb200_handle* h, const double* weights_terminal, const double* d_z, const double* d_p,
+                              double* d_out, int32_t n, void* cuda_stream);
 
 /* Introspection for benches/tests. */
 int64_t mpcb200_launch_count(const mpcb200_handle* h);       /* kernels launched by this handle so far */

@@ -30,7 +30,7 @@ class Config(C.Structure):
                  ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double), ("mu_min_alpha", C.c_double), ("mu_up_alpha", C.c_double), ("mu_up_factor", C.c_double), ("mu_max", C.c_double), ("mu_factor_full", C.c_double),
                  ("kappa_sigma", C.c_double), ("screen_inv_curv", C.c_double), ("trust_step", C.c_double), ("acc_factor", C.c_double),
                  ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32),
-                 ("mu_warm", C.c_double), ("warm_push", C.c_double), ("kappa_warm", C.c_double),
+                 ("mu_warm", C.c_double), ("warm_push", C.c_double), ("kappa_warm", C.c_double), ("stiff_slack", C.c_double),
                  ("warm_duals", C.c_int32), ("warps_per_cta", C.c_int32), ("host_route", C.c_int32), ("host_chunks", C.c_int32)])
 
 
@@ -50,6 +50,7 @@ EXPORTS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_solve_cold": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_void_p]),
     "mpcb200_solve_host": (C.c_int, [C.c_void_p] * 8 + [C.c_int32]),
+    "mpcb200_forces_stage_eval": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_launch_count": (C.c_int64, [C.c_void_p]),
     "mpcb200_workspace_words": (C.c_int32, [C.c_void_p]),
     "mpcb200_slab_in_smem": (C.c_int32, [C.c_void_p]),

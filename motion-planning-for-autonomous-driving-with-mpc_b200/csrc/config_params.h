@@ -18,6 +18,7 @@ inline ParamsT<T> params_from_config(const mpcb200_config& c) {
   p.mu0 = (T)c.mu0; p.mu_min = (T)c.mu_min; p.mu_factor = (T)c.mu_factor;
   p.tol_step = (T)c.tol_step; p.tol_feas = (T)c.tol_feas; p.tau_min = (T)c.tau_min; p.bound_push = (T)c.bound_push;
   p.acc_factor = (T)c.acc_factor; p.acc_iters = c.acc_iters; p.stall_iters = c.stall_iters; p.trust_step = (T)c.trust_step; p.screen_inv_curv = (T)c.screen_inv_curv; p.init_rollout = c.init_rollout; p.kappa_sigma = (T)c.kappa_sigma; p.mu_min_alpha = (T)c.mu_min_alpha;
+  p.stiff_slack = (T)c.stiff_slack;
   p.mu_warm = (T)c.mu_warm; p.warm_push = (T)c.warm_push; p.kappa_warm = (T)c.kappa_warm;
   p.mu_up_alpha = (T)c.mu_up_alpha; p.mu_up_factor = (T)c.mu_up_factor; p.mu_max = (T)c.mu_max; p.mu_factor_full = (T)c.mu_factor_full;
   return p;
@@ -41,7 +42,7 @@ inline void default_config(mpcb200_config* c, int N, int precision) {
   c->acc_iters = 4; c->stall_iters = 10; c->refine_f64 = (precision == MPCB200_F32) ? 1 : 0; c->trust_step = 1e-2; c->screen_inv_curv = 1e6; c->init_rollout = 0; c->kappa_sigma = 1e10; c->mu_min_alpha = 0.5;
   c->mu_up_alpha = 0.5; c->mu_up_factor = 10.0; c->mu_max = 1e3; c->mu_factor_full = 0.04;
   c->mu_warm = 1e-4; c->warm_push = 1e-6; c->kappa_warm = 1e2; c->warm_duals = 1;
-  c->warps_per_cta = 0; c->host_route = 0; c->host_chunks = 0;
+  c->warps_per_cta = 0; c->host_route = 0; c->host_chunks = 0; c->stiff_slack = 1e-3;
 }
 
 }  // namespace mpcb200

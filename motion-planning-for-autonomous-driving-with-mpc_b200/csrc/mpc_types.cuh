@@ -44,6 +44,7 @@ struct ParamsT {
   T mu_factor_full;                      // barrier reduction factor after a full (alpha = 1) primal and dual step
   T kappa_sigma;                 // multipliers are kept within [mu/(kappa s), kappa mu/s] after every step
   int init_rollout;              // 1: initial states = Euler rollout of the initial controls from the pinned state
+  T stiff_slack;                 // float32: an acceptable-level exit with a live obstacle slack below this is flagged ST_STALLED
   T mu_warm, warm_push, kappa_warm;   // dual warm start (init_warm): restart barrier parameter, interior push, multiplier band
 };
 

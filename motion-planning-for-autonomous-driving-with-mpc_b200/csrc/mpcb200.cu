@@ -26,6 +26,7 @@
 #include "config_params.h"
 #include "warp_core.cuh"
 #include "loop_core.cuh"
+#include "forces_model.cuh"
 
 using namespace mpcb200;
 
@@ -92,6 +93,7 @@ struct SolveArgs {
   int cold;             // 1: X / U are outputs only (cold start: X_0 tiled, zero controls)
   int refine;           // 1: float64 refinement pass -- the work list is q_list[0 .. q_count), warm start = the float32 X / U
   int dynamic;          // 1: B exceeds the launch's warps: warps claim further problems from ctr->next
+  int pdl_primary;      // 1: a dependent launch (the refinement pass) follows: let it get resident while this grid runs
 };
 
 // shared-memory carve-up of one CTA: [WPC slabs of T][WPC float64 xref staging blocks of (5(N+1) + 1 rounded up to even) doubles]
@@ -164,6 +166,10 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();                                  // the only CTA-wide barrier: from here on the warps are independent
+  // Programmatic dependent launch: the float32 pass lets the refinement grid become resident right away (its launch latency
+  // then hides under this grid); the refinement grid waits here until the float32 grid has completed and flushed its results.
+  if (a.pdl_primary) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.refine) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const WarpCtx w;
   T obs[6];
@@ -230,8 +236,8 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
     if (lane == 0) nxt = total_warps + atomicAdd(&a.ctr->next, 1);
     item = __shfl_sync(0xffffffffu, nxt, 0);
   }
-  // self-resetting counters: the last warp to leave zeroes what this launch used
-  if ((a.dynamic || a.refine) && lane == 0) {
+  // self-resetting counters: the last warp to leave zeroes what this launch used (an empty refinement queue used nothing)
+  if ((a.dynamic || a.refine) && lane == 0 && !(a.refine && nwork == 0)) {
     __threadfence();
     if (atomicAdd(&a.ctr->done, 1) == total_warps - 1) {
       a.ctr->next = 0; a.ctr->done = 0;
@@ -304,6 +310,28 @@ __global__ void build_ref_window_kernel(int i, int Tlen, const double* path, con
   ref_window_rows(i, N, Tlen, path, orient, vdes, x + (size_t)b * 5, xref + (size_t)b * 5 * (N + 1));
 }
 
+// FORCESPRO-formulation stage linearisation (forces_model.cuh): one thread per (z, p) point, float64, one warp per CTA.  The 136
+// output words of a point are staged through shared memory so that the global stores are coalesced.
+__global__ void __launch_bounds__(32) forces_stage_eval_kernel(ForcesConsts<double> C, const double* __restrict__ z, const double* __restrict__ p,
+                                                                 double* __restrict__ out, int n) {
+  __shared__ double stage[32 * (FORCES_OUT_WORDS + 1)];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  if (i < n) {
+    double zz[7], pp[10], o[FORCES_OUT_WORDS];
+    for (int j = 0; j < 7; ++j) zz[j] = z[(size_t)i * 7 + j];
+    for (int j = 0; j < 10; ++j) pp[j] = p[(size_t)i * 10 + j];
+    forces_stage_eval<double>(C, zz, pp, o);
+    for (int j = 0; j < FORCES_OUT_WORDS; ++j) stage[threadIdx.x * (FORCES_OUT_WORDS + 1) + j] = o[j];
+  }
+  __syncthreads();
+  const int base = blockIdx.x * 32;
+  const int cnt = min(32, n - base) * FORCES_OUT_WORDS;
+  for (int e = threadIdx.x; e < cnt; e += 32) {
+    const int r = e / FORCES_OUT_WORDS, c = e - r * FORCES_OUT_WORDS;
+    out[(size_t)base * FORCES_OUT_WORDS + e] = stage[r * (FORCES_OUT_WORDS + 1) + c];
+  }
+}
+
 // ===================================================================================================== handle
 #define MPCB200_HOST_STREAMS 4
 struct KernelPlan {     // launch shape of one kernel family (solve / refinement / closed loop) for this handle
@@ -361,8 +389,17 @@ template <typename T, int WPC, int HM>
 static cudaError_t launch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
   const int ctas = grid_for(k, nwork);
   a.dynamic = (a.refine || nwork > ctas * WPC) ? 1 : 0;
-  mpc_warp_solve_kernel<T, WPC, HM><<<ctas, 32 * WPC, k.smem, s>>>(a);
   h->launches++;
+  if (a.refine) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(32 * WPC); cfg.dynamicSmemBytes = k.smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, mpc_warp_solve_kernel<T, WPC, HM>, a);
+  }
+  mpc_warp_solve_kernel<T, WPC, HM><<<ctas, 32 * WPC, k.smem, s>>>(a);
   return cudaGetLastError();
 }
 template <typename T, int WPC, int HM>
@@ -464,7 +501,7 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   a.ctr = h->ctr;
   // a float32 handle with cfg.refine_f64 queues what it did not converge for the float64 pass that follows (fused mode only)
   a.q_list = (mode == MODE_ONESHOT && sizeof(T) == 4 && h->cfg.refine_f64 && status) ? h->q_list : nullptr;
-  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold; a.refine = 0; a.dynamic = 0;
+  a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold; a.refine = 0; a.dynamic = 0; a.pdl_primary = a.q_list ? 1 : 0;
   cudaError_t e = dispatch_solve<T>(h, a, s, h->solve, B);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel launch", e);
   return 0;
@@ -482,7 +519,7 @@ static int refine_pass(mpcb200_handle* h, const double* xref, double* X, double*
   a.Xin = X; a.Uin = U;
   a.slab = nullptr; a.state = nullptr; a.obs_shift = nullptr;
   a.ctr = h->ctr; a.q_list = h->q_list;
-  a.B = B; a.mode = MODE_ONESHOT; a.n_iter = h->cfg.max_iter; a.cold = 0; a.refine = 1; a.dynamic = 1;
+  a.B = B; a.mode = MODE_ONESHOT; a.n_iter = h->cfg.max_iter; a.cold = 0; a.refine = 1; a.dynamic = 1; a.pdl_primary = 0;
   cudaError_t e = dispatch_solve<double>(h, a, s, h->refine, B);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel<double> (refinement) launch", e);
   return 0;
@@ -736,6 +773,23 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
   for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamSynchronize(h->hs[i]));
   if (h_status) memcpy(h_status, h->h_pin, (size_t)B * 4);
   if (h_iters) memcpy(h_iters, h->h_pin + mb, (size_t)B * 4);
+  return 0;
+}
+
+int mpcb200_forces_stage_eval(mpcb200_handle* h, const double* weights_terminal, const double* d_z, const double* d_p, double* d_out, int32_t n,
+                              void* stream) {
+  if (!h) return -2;
+  if (n <= 0) return 0;
+  if (!weights_terminal || !d_z || !d_p || !d_out) { h->err = "null argument"; return -2; }
+  DeviceGuard guard(h->cfg.device);
+  ForcesConsts<double> C;
+  C.dt = h->cfg.dt; C.l_wb = h->cfg.l_wb; C.l_fric = h->cfg.l_fric; C.ego_off = h->cfg.ego_offset;
+  for (int i = 0; i < 5; ++i) { C.Q[i] = h->cfg.Q[i]; C.Pt[i] = weights_terminal[i]; }
+  C.R[0] = h->cfg.R[0]; C.R[1] = h->cfg.R[1];
+  forces_stage_eval_kernel<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(C, d_z, d_p, d_out, n);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, "forces_stage_eval launch", e);
   return 0;
 }
 

@@ -167,6 +167,8 @@ class B200Optimizer(_Base):
         for j in range(3):
             cfg.obstacle[2 * j] = float(self.obstacle_circles_centers_tuple[j][0])
             cfg.obstacle[2 * j + 1] = float(self.obstacle_circles_centers_tuple[j][1])
+        if cfg.precision == _capi.F32 and "refine_f64" not in solver_opts:
+            cfg.refine_f64 = 1 if self._obstacle_within_reach() else 0
         _capi.set_options(cfg, solver_opts)            # raises on a name that is not a field of mpcb200_config
         self.cfg = cfg
         self.N = N
@@ -175,6 +177,22 @@ class B200Optimizer(_Base):
         self._path_d = None
 
     # ------------------------------------------------------------------ helpers
+    OBSTACLE_REACH_M = 25.0
+
+    def _obstacle_within_reach(self):
+        """The float64 refinement pass exists for ACTIVE obstacle rows (float32 stalls on their stiff barrier weights, status 3).
+        A row can only become active where the ego can touch the obstacle: if every point of the reference path keeps more than
+        OBSTACLE_REACH_M + r_ego + r_obs from every obstacle circle (lane following: the reference's dummy obstacle at (-100, 0),
+        quirk Q11), the pass could never find work and its (empty) launch is skipped.  The library default is refine_f64 = 1;
+        pass refine_f64=... to override this decision either way."""
+        path = np.asarray(self.resampled_path_points, float)[:, :2]
+        r = float(self.radius_ego + self.radius_obstacle) + self.OBSTACLE_REACH_M
+        pts = np.vstack([path, np.array([[self.init_position[0], self.init_position[1]]], float)])
+        for c in self.obstacle_circles_centers_tuple:
+            if np.hypot(pts[:, 0] - float(c[0]), pts[:, 1] - float(c[1])).min() <= r:
+                return True
+        return False
+
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
@@ -276,6 +294,26 @@ class B200Optimizer(_Base):
         h.check(h.lib.mpcb200_solve_host(h.h, ptr(xref), ptr(X_in) if not cold else None, ptr(U_in) if not cold else None,
                                          ptr(X), ptr(U), ptr(status), ptr(iters), B))
         return U, X, status, iters
+
+    def forces_stage_eval(self, z, p, weights_terminal=None):
+        """Stage functions + first derivatives of the reference's FORCESPRO formulation (optimizer.py:90-195) for n points:
+        z [n,7], p [n,10] -> dict(c[n,5], dc[n,5,7], h[n,10], dh[n,10,7], f[n], df[n,7], fN[n], dfN[n,7]) as CUDA tensors.
+        `weights_terminal`: the five weight_*_terminate values (default: from weights_setting)."""
+        import ctypes
+        t = self.torch
+        z, p = self._dev(z), self._dev(p)
+        n = z.shape[0]
+        assert z.shape == (n, 7) and p.shape == (n, 10)
+        if weights_terminal is None:
+            w = self.weights_setting
+            weights_terminal = [w[k] for k in ("weight_x_terminate", "weight_y_terminate", "weight_steering_angle_terminate",
+                                               "weight_velocity_terminate", "weight_heading_angle_terminate")]
+        wt = (ctypes.c_double * 5)(*[float(v) for v in weights_terminal])
+        out = t.empty(n, 136, dtype=t.float64, device=self.device)
+        h = self.handle
+        h.check(h.lib.mpcb200_forces_stage_eval(h.h, wt, z.data_ptr(), p.data_ptr(), out.data_ptr(), n, self._stream()))
+        return dict(c=out[:, 0:5], dc=out[:, 5:40].reshape(n, 5, 7), h=out[:, 40:50], dh=out[:, 50:120].reshape(n, 10, 7),
+                    f=out[:, 120], df=out[:, 121:128], fN=out[:, 128], dfN=out[:, 129:136])
 
     def plant_step_shift(self, x, U, X):
         """shift_movement (optimizer.py:645-655) on the device, in place.  Returns applied controls [B,2]."""

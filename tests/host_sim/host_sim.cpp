@@ -9,6 +9,7 @@
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/config_params.h"
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/warp_core.cuh"
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/loop_core.cuh"
+#include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/forces_model.cuh"
 
 using namespace mpcb200;
 
@@ -106,6 +107,14 @@ int hostsim_closed_loop(const mpcb200_config* cfg, int iter_length, const double
   d.desired_velocity = vdes; d.l_wb = cfg->l_wb; d.dt = cfg->dt; d.B = B; d.Tlen = iter_length; d.warm_duals = cfg->warm_duals;
   if (cfg->precision == MPCB200_F64) run_loop<double>(*cfg, d); else run_loop<float>(*cfg, d);
   return 0;
+}
+// FORCESPRO-formulation stage functions (csrc/forces_model.cuh) in float64: consts = [dt, l_wb, l_fric, ego_off, Q5, R2, Pt5]
+void hostsim_forces_eval(const double* consts, const double* z, const double* p, double* out, int n) {
+  ForcesConsts<double> C;
+  C.dt = consts[0]; C.l_wb = consts[1]; C.l_fric = consts[2]; C.ego_off = consts[3];
+  for (int i = 0; i < 5; ++i) { C.Q[i] = consts[4 + i]; C.Pt[i] = consts[11 + i]; }
+  C.R[0] = consts[9]; C.R[1] = consts[10];
+  for (int i = 0; i < n; ++i) forces_stage_eval<double>(C, z + 7 * i, p + 10 * i, out + FORCES_OUT_WORDS * i);
 }
 void hostsim_trace_step(int i) { mpc_trace_step = i; }
 void hostsim_default_config(mpcb200_config* c, int N, int precision) { default_config(c, N, precision); }

@@ -20,7 +20,7 @@ class Config(C.Structure):
                  ("tol_feas", C.c_double), ("tau_min", C.c_double), ("bound_push", C.c_double), ("mu_min_alpha", C.c_double), ("mu_up_alpha", C.c_double), ("mu_up_factor", C.c_double), ("mu_max", C.c_double), ("mu_factor_full", C.c_double),
                  ("kappa_sigma", C.c_double), ("screen_inv_curv", C.c_double), ("trust_step", C.c_double), ("acc_factor", C.c_double),
                  ("acc_iters", C.c_int32), ("stall_iters", C.c_int32), ("refine_f64", C.c_int32), ("init_rollout", C.c_int32),
-                 ("mu_warm", C.c_double), ("warm_push", C.c_double), ("kappa_warm", C.c_double),
+                 ("mu_warm", C.c_double), ("warm_push", C.c_double), ("kappa_warm", C.c_double), ("stiff_slack", C.c_double),
                  ("warm_duals", C.c_int32), ("warps_per_cta", C.c_int32), ("host_route", C.c_int32), ("host_chunks", C.c_int32)])
 
 
@@ -33,7 +33,7 @@ def lib():
         so = os.path.join(HERE, "libhostsim.so")
         src = os.path.join(HERE, "host_sim.cpp")
         csrc = os.path.join(HERE, "..", "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "loop_core.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "loop_core.cuh", "forces_model.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
         if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMPC_DIAG", "-shared", "-fPIC", "-o", so, src], cwd=HERE)
         _lib = C.CDLL(so)
@@ -71,3 +71,24 @@ def closed_loop(cfg, sc, x0):
     lib().hostsim_closed_loop.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5 + [C.c_int]
     lib().hostsim_closed_loop(C.byref(cfg), T, p(path), p(orient), float(sc.desired_velocity), p(x0), p(traj), p(ctrl), p(st), p(it), B)
     return traj, ctrl, st, it
+
+
+FORCES_OUT_WORDS = 136
+
+
+def unpack_forces(out):
+    """[n,136] -> dict(c[n,5], dc[n,5,7], h[n,10], dh[n,10,7], f[n], df[n,7], fN[n], dfN[n,7]) (csrc/forces_model.cuh layout)."""
+    out = np.asarray(out)
+    n = out.shape[0]
+    return dict(c=out[:, 0:5], dc=out[:, 5:40].reshape(n, 5, 7), h=out[:, 40:50], dh=out[:, 50:120].reshape(n, 10, 7),
+                f=out[:, 120], df=out[:, 121:128], fN=out[:, 128], dfN=out[:, 129:136])
+
+
+def forces_eval(consts, z, p):
+    z = np.ascontiguousarray(z, np.float64); p = np.ascontiguousarray(p, np.float64)
+    consts = np.ascontiguousarray(consts, np.float64)
+    n = z.shape[0]
+    out = np.zeros((n, FORCES_OUT_WORDS))
+    q = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hostsim_forces_eval(q(consts), q(z), q(p), q(out), n)
+    return unpack_forces(out)
