@@ -288,6 +288,11 @@ struct WarpSolver {
     w.sync();
   }
 
+  // Feasibility tolerance of the PINNED stage: in a closed loop the pinned state is the plant's answer to the previous solution,
+  // which sits ON its active bounds up to the rounding of the arithmetic (float32: delta_1 = delta_max + 1 ulp would otherwise
+  // flag every later MPC step ST_INFEASIBLE_X0 -- measured: 19 % of the float32 Lanker closed-loop steps).
+  MPC_HD static T x0_tol() { return sizeof(T) == 4 ? T(2e-5) : T(1e-9); }
+
   // ---------------------------------------------------------------- initialisation (lane = stage)
   // Pushes the start point strictly inside the bounds and puts slacks / multipliers on the central path; fills the
   // trig cache.  Every lane ends with the same (uniform) ProbState.
@@ -303,12 +308,12 @@ struct WarpSolver {
     const T amax0 = m_sqrt(m_max(P.a_max - s0, T(1e-12)));
     st.a0_hi = m_min(amax0, P.a_max);
     st.a0_lo = -amax0;
-    if (de0 < P.de_min || de0 > P.de_max || v0 < P.v_min || v0 > P.v_max) bad = true;
+    if (de0 < P.de_min - x0_tol() || de0 > P.de_max + x0_tol() || v0 < P.v_min - x0_tol() || v0 > P.v_max + x0_tol()) bad = true;
     {
       T sn, cs; m_sincos(xa(0, 4), &sn, &cs);
       for (int j = 0; j < 3; ++j) {
         T h, gx, gy, gp; obst(j, xa(0, 0), xa(0, 1), sn, cs, h, gx, gy, gp);
-        if (h < P.r_sum) bad = true;
+        if (h < P.r_sum - x0_tol()) bad = true;
       }
     }
     if (bad) { st.status = ST_INFEASIBLE_X0; st.done = 1; }
@@ -503,12 +508,12 @@ struct WarpSolver {
     const T amax0 = m_sqrt(m_max(P.a_max - s0, T(1e-12)));
     st.a0_hi = m_min(amax0, P.a_max);
     st.a0_lo = -amax0;
-    if (de0 < P.de_min || de0 > P.de_max || v0 < P.v_min || v0 > P.v_max) bad = true;
+    if (de0 < P.de_min - x0_tol() || de0 > P.de_max + x0_tol() || v0 < P.v_min - x0_tol() || v0 > P.v_max + x0_tol()) bad = true;
     {
       T sn, cs; m_sincos(xa(0, 4), &sn, &cs);
       for (int j = 0; j < 3; ++j) {
         T h, gx, gy, gp; obst(j, xa(0, 0), xa(0, 1), sn, cs, h, gx, gy, gp);
-        if (h < P.r_sum) bad = true;
+        if (h < P.r_sum - x0_tol()) bad = true;
       }
     }
     if (bad) { st.status = ST_INFEASIBLE_X0; st.done = 1; }
@@ -678,19 +683,21 @@ struct WarpSolver {
     const T* pe0 = &sl[last + tb.e[0]]; const T* pe1 = &sl[last + tb.e[1]]; const T* pe2 = &sl[last + tb.e[2]];
     const T* pr = &sl[last + R_RU];
     T* pk = &sl[last + R_KK + tb.j];
-    auto fetch = [&](BwdCoef& q) {
+    // loads the record the pointers stand on, then steps them one record down -- except below record 0 (`step` = 0 there: the
+    // last prefetch re-reads record 0 instead of reading below the records; branch-free, a uniform select on the bump)
+    auto fetch = [&](BwdCoef& q, int step) {
       q.h = *ph; q.c0 = *pc0; q.c1 = *pc1; q.c2 = *pc2; q.c3 = *pc3; q.c4 = *pc4; q.e0 = *pe0; q.e1 = *pe1; q.e2 = *pe2;
       q.Ru0 = pr[0]; q.Ru1 = pr[1]; q.rp0 = pr[2]; q.rp1 = pr[3];
-      ph -= RS; pc0 -= RS; pc1 -= RS; pc2 -= RS; pc3 -= RS; pc4 -= RS;
-      pe0 -= RS; pe1 -= RS; pe2 -= RS; pr -= RS;
+      ph -= step; pc0 -= step; pc1 -= step; pc2 -= step; pc3 -= step; pc4 -= step;
+      pe0 -= step; pe1 -= step; pe2 -= step; pr -= step;
     };
-    auto stage = [&](int k, const BwdCoef& cur, BwdCoef& nxt, bool more) -> bool {
+    auto stage = [&](int k, const BwdCoef& cur, BwdCoef& nxt) -> bool {
       Pij += cur.h;                                   // x_{k+1} terms
       // round 1: control block + M = [P|p] * Atilde
       const T p22 = w.shfl(Pij, 14), p23 = w.shfl(Pij, 15), p33 = w.shfl(Pij, 21);
       const T q0 = w.shfl(Pij, tb.s1[0]), q1 = w.shfl(Pij, tb.s1[1]), q2 = w.shfl(Pij, tb.s1[2]);
       const T q3 = w.shfl(Pij, tb.s1[3]), q4 = w.shfl(Pij, tb.s1[4]);
-      if (more) fetch(nxt);   // next stage's record, off the dependent chain (uniform predicate: nothing is read below stage 0)
+      fetch(nxt, k >= 2 ? RS : 0);   // record k-1, off the dependent chain (at k = 0: record 0 once more, never below the records)
       const T M = ownf * Pij + ((cur.c0 * q0 + cur.c1 * q1) + (cur.c2 * q2 + cur.c3 * q3) + cur.c4 * q4);
       // G / dt^2 (the stored control diagonal is pre-divided): J = -dt^2 G^-1 = -(G / dt^2)^-1 needs no dt^2 on the chain
       const T G00 = cur.Ru0 + p22, G01 = p23, G11 = cur.Ru1 + p33;
@@ -736,13 +743,13 @@ struct WarpSolver {
     };
     // two stages per trip with ping-pong coefficient registers (no register moves between stages)
     BwdCoef ca, cb;
-    fetch(ca);
+    fetch(ca, N >= 2 ? RS : 0);
     int k = N - 1;
     for (; k >= 1; k -= 2) {
-      if (!stage(k, ca, cb, true)) { ok = false; break; }
-      if (!stage(k - 1, cb, ca, k - 1 > 0)) { ok = false; break; }
+      if (!stage(k, ca, cb)) { ok = false; break; }
+      if (!stage(k - 1, cb, ca)) { ok = false; break; }
     }
-    if (ok && k == 0) ok = stage(0, ca, cb, false);
+    if (ok && k == 0) ok = stage(0, ca, cb);
     w.sync();
     return ok;
   }
@@ -766,11 +773,13 @@ struct WarpSolver {
     const T* pf0 = &sl[L.o_rec + tb.fc[0]]; const T* pf1 = &sl[L.o_rec + tb.fc[1]]; const T* pf2 = &sl[L.o_rec + tb.fc[2]];
     const T* pf3 = &sl[L.o_rec + tb.fc[3]]; const T* pf4 = &sl[L.o_rec + tb.fc[4]]; const T* pfc = &sl[L.o_rec + tb.fc0];
     T* pd = &sl[L.o_rec + row];
-    auto fetch = [&](FwdCoef& q) {
-      q.f0 = *pf0; q.f1 = *pf1; q.f2 = *pf2; q.f3 = *pf3; q.f4 = *pf4; q.fc = *pfc; q.d = pd[R_D];
-      pf0 += RS; pf1 += RS; pf2 += RS; pf3 += RS; pf4 += RS; pfc += RS;
+    const T* pl = &sl[L.o_rec + row];
+    // loads record j (where the pointers stand), then steps them up -- except past the last record (`step` = 0 there)
+    auto fetch = [&](FwdCoef& q, int step) {
+      q.f0 = *pf0; q.f1 = *pf1; q.f2 = *pf2; q.f3 = *pf3; q.f4 = *pf4; q.fc = *pfc; q.d = pl[R_D];
+      pf0 += step; pf1 += step; pf2 += step; pf3 += step; pf4 += step; pfc += step; pl += step;
     };
-    auto stage = [&](const FwdCoef& cur, FwdCoef& nxt, bool more) {
+    auto stage = [&](int k, const FwdCoef& cur, FwdCoef& nxt) {
       const T acc = (cur.fc + cur.f0 * dx0) + (cur.f1 * dx1 + cur.f2 * dx2) + (cur.f3 * dx3 + cur.f4 * dx4);
       const T nx = (mine + cur.d) + acc;
       dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);
@@ -778,13 +787,13 @@ struct WarpSolver {
       if (lane < 5) pd[R_DX] = nx;
       if (lane == 2 || lane == 3) pd[R_DU - 2] = acc * idt;
       pd += RS;
-      if (more) fetch(nxt);   // uniform predicate: nothing is read past the last record
+      fetch(nxt, k + 2 < N ? RS : 0);   // record k+1 (at k = N-1: record N-1 once more, never past the last record)
     };
     FwdCoef ca, cb;
-    fetch(ca);
+    fetch(ca, N >= 2 ? RS : 0);
     int k = 0;
-    for (; k + 1 < N; k += 2) { stage(ca, cb, true); stage(cb, ca, k + 2 < N); }
-    if (k < N) stage(ca, cb, false);
+    for (; k + 1 < N; k += 2) { stage(k, ca, cb); stage(k + 1, cb, ca); }
+    if (k < N) stage(k, ca, cb);
     w.sync();
   }
 

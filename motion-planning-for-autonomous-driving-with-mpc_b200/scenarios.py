@@ -38,7 +38,8 @@ def load_scenario(name):
                            orientation=np.array(d["orientation"], float), desired_velocity=float(d["desired_velocity"]),
                            iter_length=int(d["iter_length"]), dt=float(d["dt"]), weights_setting=dict(d["weights_setting"]),
                            static_obstacle=dict(d["static_obstacle"]), use_case=d["use_case"],
-                           wheelbase=float(d.get("wheelbase", 2.578)), synthesised=bool(d.get("synthesised", False)))
+                           wheelbase=float(d.get("wheelbase", 2.578)), synthesised=bool(d.get("synthesised", False)),
+                           origin_reference_path=(np.array(d["origin_reference_path"], float) if "origin_reference_path" in d else None))
 
 
 def perturbed_initial_states(sc, B, seed, r_clear=None, obstacle_circles=None, ego_offset=0.75):

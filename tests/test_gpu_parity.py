@@ -355,7 +355,8 @@ def test_host_path_zero_copy_route_is_bit_identical_to_the_staged_route_and_the_
     assert np.array_equal(Up, Ua) and np.array_equal(Xp, Xa) and np.array_equal(itp, ita)
 
 
-@pytest.mark.parametrize("key,name,sigma", [("casadi_zam_lf", "ZAM_Over-1_1_LF", 0.1), ("casadi_zam_ca", "ZAM_Over-1_1_CA", 0.05)])
+@pytest.mark.parametrize("key,name,sigma", [("casadi_zam_lf", "ZAM_Over-1_1_LF", 0.1), ("casadi_zam_ca", "ZAM_Over-1_1_CA", 0.05),
+                                            ("casadi_lanker_lf", "USA_Lanker-2_18_T-1_LF", 0.1)])
 def test_recorded_ipopt_controls_pin_the_gpu_optimum_statistically(key, name, sigma):
     """The reference's recorded CasADi/IPOPT closed loops (N = 10, u applied = u*_0 + N(0, sigma^2)) against the CUDA
     solver: all recorded states of a run are solved as ONE batch (each with the window of its own MPC step); the

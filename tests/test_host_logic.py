@@ -104,7 +104,7 @@ def test_scenarios_and_batch_generator():
     names = mpc_b200.scenario_names()
     assert {"ZAM_Over-1_1_LF", "ZAM_Over-1_1_CA", "USA_Lanker-2_18_T-1_LF"} <= set(names)
     sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
-    assert sc.iter_length == 30 and abs(sc.desired_velocity - 19.9991) < 1e-9 and sc.dt == 0.1
+    assert sc.iter_length == 30 and abs(sc.desired_velocity - 19.9995) < 1e-9 and sc.dt == 0.1
     assert np.allclose(sc.reference_path[0], [29.9948, -1.1501]) and np.allclose(sc.reference_path[-1], [87.8, 3.3])
     assert mpc_b200.load_scenario("USA_Lanker-2_18_T-1_LF").iter_length == 70
     a = mpc_b200.make_batch("ZAM_Over-1_1_LF", 64, 30, 20261017)

@@ -169,7 +169,8 @@ def test_reference_window_rule_q8():
     assert np.all(w30[1:, 0] == np.arange(0, 30))
 
 
-@pytest.mark.parametrize("key,name,sigma", [("casadi_zam_lf", "ZAM_Over-1_1_LF", 0.1), ("casadi_zam_ca", "ZAM_Over-1_1_CA", 0.05)])
+@pytest.mark.parametrize("key,name,sigma", [("casadi_zam_lf", "ZAM_Over-1_1_LF", 0.1), ("casadi_zam_ca", "ZAM_Over-1_1_CA", 0.05),
+                                            ("casadi_lanker_lf", "USA_Lanker-2_18_T-1_LF", 0.1)])
 def test_recorded_ipopt_controls_pin_the_oracle_optimum_statistically(key, name, sigma):
     """SURVEY 8c (6), extended to every recorded step.  The reference's recorded CasADi/IPOPT closed loops (N = 10,
     /root/reference/test/2D_plots_casadi_ZAM_Over-1_1_*/) applied u = u*_0 + N(0, sigma^2) (optimizer.py:611-617) at the
@@ -177,7 +178,10 @@ def test_recorded_ipopt_controls_pin_the_oracle_optimum_statistically(key, name,
     u_rec - u*_0(oracle) that look like that noise: zero median within its standard error, robust spread = sigma.
     A wrong cost pairing (Q2), a terminal cost (Q1), a wrong window (Q8) or friction row (Q3) shifts u*_0 by far more.
     A few steps are outliers in the RECORDING (IPOPT's return status is never checked, optimizer.py:607-609), so the
-    statistics are robust ones.  (The Lanker run is not used: its route-planner path is only approximately restated.)"""
+    statistics are robust ones.  All three recorded CasADi runs are used: since the route planner's reference path is restated
+    exactly (tests/test_results_format.py) the 70-step USA_Lanker run -- different weights, a left turn and two lane changes,
+    both friction-limited phases -- pins the NLP as well as the two ZAM_Over runs (residual mean 0.015 / 0.000, spread 0.10 / 0.085
+    for sigma = 0.1; with the approximate path of round 1 the acceleration residual had a mean of +0.23)."""
     import mpc_b200
     from oracle import ipm
     g = np.load(os.path.join(G, "recorded_runs.npz"))

@@ -8,7 +8,8 @@ package (`<pkg>/data/scenarios.json`).  Nothing at run time on the GPU box reads
 It restates what `Configuration.find_reference_path_and_desired_velocity` does
 (/root/reference/MPC_Planner/configuration.py:499-552) without commonroad:
 
-  route reference path  -> centre line of the route lanelets ((left+right)/2 per vertex)
+  route reference path  -> `route_reference_path`: centre lines ((left+right)/2 per vertex) of the route lanelets, resampled,
+                           lane changes ramped, smoothed -- the route planner's construction, pinned by the recorded deviation.txt
   clip_reference_path   -> configuration.py:584-623 (restated in `clip_reference_path`)
   desired_velocity      -> configuration.py:538-544 (length / ((T_end-1)*dt), rounded up to 1e-4)
   chaikins_corner_cutting + resample_polyline(step=v_des*dt) -> configuration.py:547-549
@@ -229,41 +230,54 @@ def route_lanelets(sc):
     return [start_lanelets(sc)[0]]
 
 
-def _by_arclength(c, n):
-    s = np.concatenate([[0], np.cumsum(np.linalg.norm(np.diff(c, axis=0), axis=1))])
-    t = np.linspace(0, s[-1], n)
-    return np.stack([np.interp(t, s, c[:, 0]), np.interp(t, s, c[:, 1])], axis=1)
+def route_reference_path(sc, chain, step_resample=1.0, num_vertices_lane_change_max=6, percentage_vertices_lane_change_max=0.1,
+                         step_final=2.0, refinements=4):
+    """The route planner's reference path for a lanelet route, restated (commonroad-route-planner is not installed here):
 
+      1. every lanelet's centre line is resampled at 1 m;
+      2. a run of lane changes (next lanelet laterally adjacent instead of a successor, e.g. Lanker 3452 -> 3454 -> 3456) shares
+         the run's length evenly: lanelet k of n contributes the vertices of its k-th n-th, minus a few vertices
+         (min(int(0.1 * n_vertices) + 1, 6)) at each junction so that the change is a ramp, not a step;
+      3. the concatenation is resampled at 2 m and smoothed by four rounds of Chaikin corner cutting.
 
-def route_reference_path(sc, chain):
-    """Centre lines of the route lanelets, concatenated.  A run of laterally adjacent lanelets
-    (lane changes, e.g. Lanker 3452 -> 3454 -> 3456) is blended linearly from the first to the last
-    centre line over the run's length -- a reconstruction, the route planner's own lane-change
-    path is not reproducible without the package (stated in DESIGN.md)."""
+    PINNED BY THE REFERENCE'S OWN RECORDINGS: `deviation.txt` (mpc_planner.py:190-197) is the distance of every recorded state to
+    the closest VERTEX of exactly this path.  With the constants above all six recorded files (ZAM_Over lane following /
+    collision avoidance and USA_Lanker lane following, CasADi and Forcespro runs, 260 values) are reproduced to < 1e-4
+    (tests/test_results_format.py); any other resampling step, vertex allowance or number of Chaikin rounds misses by 0.03 m or
+    more (scan in profiles/r02_summary.md)."""
     L = sc["lanelets"]
-    groups = [[chain[0]]]
-    for a, b in zip(chain[:-1], chain[1:]):
-        if b in L[a]["adj"] and b not in L[a]["succ"]:
-            groups[-1].append(b)
+    instr = [1 if (b in L[a]["adj"] and b not in L[a]["succ"]) else 0 for a, b in zip(chain[:-1], chain[1:])] + [0]
+    portions = [None] * len(chain)
+    i = 0
+    while i < len(chain):
+        if instr[i] == 0:
+            portions[i] = (0.0, 1.0)
+            i += 1
         else:
-            groups.append([b])
-    pts = []
-    for g in groups:
-        if len(g) == 1:
-            c = L[g[0]]["center"]
-        else:
-            n = 41
-            cs = [_by_arclength(L[i]["center"], n) for i in g]
-            w = np.linspace(0, len(g) - 1, n)
-            c = np.zeros((n, 2))
+            j = i
+            while instr[j] == 1:
+                j += 1
+            n = j - i + 1                                  # lanelets i..j share [0, 1]
             for k in range(n):
-                i0 = min(int(np.floor(w[k])), len(g) - 2)
-                f = w[k] - i0
-                c[k] = (1 - f) * cs[i0][k] + f * cs[i0 + 1][k]
-        for q in c:
-            if not pts or np.linalg.norm(q - pts[-1]) > 1e-9:
-                pts.append(q)
-    return np.array(pts)
+                portions[i + k] = (k / n, (k + 1) / n)
+            i = j + 1
+    ref = None
+    for idx, lid in enumerate(chain):
+        v = resample_polyline(L[lid]["center"], step_resample)
+        nv = len(v)
+        nlc = min(int(nv * percentage_vertices_lane_change_max) + 1, num_vertices_lane_change_max)
+        last = idx == len(chain) - 1
+        if ref is None:
+            i0, i1 = int(portions[idx][0] * nv), max(int(portions[idx][1] * nv), 1)
+            if not last:
+                i1 = max(i1 - nlc, 1)
+            ref = v[i0:i1]
+        else:
+            i0, i1 = min(int(portions[idx][0] * nv) + nlc, nv - 1), int(portions[idx][1] * nv)
+            if not last:
+                i1 = max(i1 - nlc, 1)
+            ref = np.concatenate([ref, v[i0:i1]])
+    return chaikins_corner_cutting(resample_polyline(ref, step_final), refinements)
 
 
 # ---------------------------------------------------------------- weights
@@ -310,6 +324,7 @@ def build(name, xml, yaml_rel, use_case, synth=False):
     return dict(name=name, xml=xml, use_case=use_case, synthesised=synth, dt=dt,
                 x0=[sc["init"]["x"], sc["init"]["y"], 0.0, sc["init"]["v"], sc["init"]["psi"]],
                 route_lanelets=chain, desired_velocity=v_des, iter_length=int(path.shape[0]),
+                origin_reference_path=origin.tolist(),
                 reference_path=path.tolist(), orientation=orient.tolist(),
                 clipped_length=length, static_obstacle=obstacle,
                 weights_setting={k: float(v) for k, v in settings["weights_setting"].items()},
