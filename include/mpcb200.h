@@ -99,6 +99,17 @@ const char* mpcb200_last_error(const mpcb200_handle* h);   /* h may be NULL: err
 int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U,
                   int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
+/* Same solve with the inequality multipliers in and out (SURVEY 8b `d_lam`; IPOPT's `lam_x` / `lam_g` of the bound and obstacle
+ * rows, which the reference never reads, optimizer.py:609).  d_lam [B][mpcb200_lam_words] float64, per problem:
+ *   [N][14]  stage k: multipliers of deltaDot >= min, <= max, a <= a_max, a >= -sqrt(a_max - s0) (stage 0 only: friction row),
+ *            delta_{k+1} >= min, <= max, v_{k+1} >= min, <= max, the three obstacle rows of x_{k+1}; then their three slacks
+ *   [1]      barrier parameter at exit          [1]  1.0 = block valid
+ * OUT: always written.  IN: a valid block (from a previous call, shifted by the caller as it shifts X / U) warm-starts slacks
+ * and multipliers and restarts the barrier at cfg.mu_warm instead of cfg.mu0; anything else (e.g. zeros) = cold duals. */
+int mpcb200_solve_dual(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, double* d_lam,
+                       int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
+int32_t mpcb200_lam_words(const mpcb200_handle* h);          /* 14 N + 2 */
+
 /* Same solve from the reference's step-0 initial guess (X_0 tiled, zero controls, optimizer.py:578-583): d_X / d_U are
  * outputs only, nothing but d_xref is read. */
 int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U,

@@ -40,6 +40,8 @@ EXPORTS = {
     "mpcb200_destroy": (None, [C.c_void_p]),
     "mpcb200_last_error": (C.c_char_p, [C.c_void_p]),
     "mpcb200_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mpcb200_solve_dual": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
+    "mpcb200_lam_words": (C.c_int32, [C.c_void_p]),
     "mpcb200_sqp_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_sqp_iter": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_sqp_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -41,7 +41,7 @@ inline void default_config(mpcb200_config* c, int N, int precision) {
   else                          { c->mu_min = 1e-7; c->tol_step = 2e-5; c->tol_feas = 1e-4; c->acc_factor = 5.0; }   // mu_min: a weakly active row ends s ~ sqrt(mu_min / h) inside its bound (5e-4 at h = 0.4; 1.6e-3 at 1e-6)
   c->acc_iters = 4; c->stall_iters = 10; c->refine_f64 = (precision == MPCB200_F32) ? 1 : 0; c->trust_step = 1e-2; c->screen_inv_curv = 1e6; c->init_rollout = 0; c->kappa_sigma = 1e10; c->mu_min_alpha = 0.5;
   c->mu_up_alpha = 0.5; c->mu_up_factor = 10.0; c->mu_max = 1e3; c->mu_factor_full = 0.04;
-  c->mu_warm = 1e-4; c->warm_push = 1e-6; c->kappa_warm = 1e2; c->warm_duals = 1;
+  c->mu_warm = 1e-4; c->warm_push = 1e-6; c->kappa_warm = 1e2; c->warm_duals = 0;
   c->warps_per_cta = 0; c->host_route = 0; c->host_chunks = 0; c->stiff_slack = 1e-3;
 }
 

@@ -82,6 +82,7 @@ struct SolveArgs {
   const double* Uin;
   int* status;          // [B]
   int* iters;           // [B]
+  double* lam;          // [B][14N+2] inequality multipliers / obstacle slacks in and out (mpcb200_solve_dual), or null
   T* slab;              // global image of the slabs [B][words] (stepwise mode)
   ProbState<T>* state;  // [B] (stepwise mode)
   T* obs_shift;         // [B][6] shifted obstacle centres (stepwise mode)
@@ -187,7 +188,9 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
     if (need_xref) xr = fetch_xref(a.xref + (size_t)b * nx, sm.xstg(wid), nx, &bar_x[wid], ph_x, lane);
     if (need_init) {
       S.load(xr, need_warm ? a.Xin + (size_t)b * nx : nullptr, need_warm ? a.Uin + (size_t)b * nu : nullptr, a.obstacle, obs);
-      S.init(st);
+      double* const lam_b = a.lam ? a.lam + (size_t)b * WarpSolver<T, HM>::lam_words(N) : nullptr;
+      if (lam_b && need_warm && !a.refine && S.duals_valid(lam_b)) { S.load_duals(lam_b); S.init_warm(st); }   // dual warm start
+      else S.init(st);
     } else {
       // resume: the slab image comes back by one TMA bulk copy, the per-problem scalars by plain loads
       fence_async_smem();
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
     if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
       // solution back to float64 row-major (rho is added back in float64): coalesced stores straight from the slab
       S.store(xr, a.X + (size_t)b * nx, a.U + (size_t)b * nu);
+      if (a.lam) S.store_duals(a.lam + (size_t)b * WarpSolver<T, HM>::lam_words(N), st.mu);
       if (lane == 0) {
         if (a.status) a.status[b] = st.status;
         if (a.iters) a.iters[b] = st.iters + (a.refine ? a.iters[b] : 0);
@@ -487,7 +491,7 @@ static int ensure_stepwise_scratch(mpcb200_handle* h) {
 
 template <typename T>
 static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref, double* X, double* U, int* status, int* iters,
-                    int B, cudaStream_t s, int cold = 0, const double* Xin = nullptr, const double* Uin = nullptr) {
+                    int B, cudaStream_t s, int cold = 0, const double* Xin = nullptr, const double* Uin = nullptr, double* lam = nullptr) {
   if (B <= 0) return 0;
   if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
   if (((uintptr_t)xref | (uintptr_t)X | (uintptr_t)U | (uintptr_t)Xin | (uintptr_t)Uin) & 7u) { h->err = "float64 arrays must be 8-byte aligned"; return -2; }
@@ -495,7 +499,7 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   SolveArgs<T> a;
   a.P = params_from_config<T>(h->cfg);
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
-  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
+  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters; a.lam = lam;
   a.Xin = Xin ? Xin : X; a.Uin = Uin ? Uin : U;
   a.slab = (T*)h->slab; a.state = (ProbState<T>*)h->state; a.obs_shift = (T*)h->obs_shift;
   a.ctr = h->ctr;
@@ -510,12 +514,13 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
 // second pass of a float32 handle with cfg.refine_f64: float64 arithmetic (float32 tolerances) on the instances the float32
 // pass queued (status other than 1), warm-started from their float32 result.  A small persistent grid: the queue is usually
 // short or empty (then every warp leaves after one load).
-static int refine_pass(mpcb200_handle* h, const double* xref, double* X, double* U, int* status, int* iters, int B, cudaStream_t s) {
+static int refine_pass(mpcb200_handle* h, const double* xref, double* X, double* U, int* status, int* iters, int B, cudaStream_t s,
+                       double* lam = nullptr) {
   if (!status) return 0;                                // without a status buffer nothing was queued
   SolveArgs<double> a;
   a.P = params_from_config<double>(h->cfg);
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
-  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
+  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters; a.lam = lam;
   a.Xin = X; a.Uin = U;
   a.slab = nullptr; a.state = nullptr; a.obs_shift = nullptr;
   a.ctr = h->ctr; a.q_list = h->q_list;
@@ -527,10 +532,10 @@ static int refine_pass(mpcb200_handle* h, const double* xref, double* X, double*
 
 // one solve (+ the float64 refinement pass of a refine_f64 handle) with separate warm-start-in and result-out arrays
 static int solve_io(mpcb200_handle* h, const double* xref, const double* Xin, const double* Uin, double* X, double* U,
-                    int32_t* status, int32_t* iters, int32_t B, cudaStream_t s, int cold) {
-  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin);
-  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin);
-  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, xref, X, U, status, iters, B, s);
+                    int32_t* status, int32_t* iters, int32_t B, cudaStream_t s, int cold, double* lam = nullptr) {
+  if (h->cfg.precision == MPCB200_F64) return do_solve<double>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin, lam);
+  int rc = do_solve<float>(h, MODE_ONESHOT, h->cfg.max_iter, xref, X, U, status, iters, B, s, cold, Xin, Uin, lam);
+  if (rc == 0 && h->cfg.refine_f64 && B > 0) rc = refine_pass(h, xref, X, U, status, iters, B, s, lam);
   return rc;
 }
 
@@ -559,7 +564,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   mpcb200_handle* h = nullptr;
   if (!cfg || !out) { g_create_err = "null argument"; return -2; }
   if (cfg->abi_version != MPCB200_ABI_VERSION) { g_create_err = "abi_version mismatch"; return -2; }
-  if (cfg->N < 4 || cfg->N > 512 || cfg->max_batch < 1) { g_create_err = "N must be in [4, 512], max_batch >= 1"; return -2; }
+  if (cfg->N < 4 || cfg->N > 128 || cfg->max_batch < 1) { g_create_err = "N must be in [4, 128] (tested range), max_batch >= 1"; return -2; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) { fail(nullptr, "no CUDA device (libmpcb200 has no CPU path)", e); return -3; }
@@ -622,6 +627,17 @@ int mpcb200_solve(mpcb200_handle* h, const double* d_xref, double* d_X, double* 
   DeviceGuard guard(h->cfg.device);
   return solve_io(h, d_xref, nullptr, nullptr, d_X, d_U, d_status, d_iters, B, (cudaStream_t)stream, 0);
 }
+
+int mpcb200_solve_dual(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, double* d_lam, int32_t* d_status, int32_t* d_iters,
+                       int32_t B, void* stream) {
+  if (!h) return -2;
+  if (!d_lam) { h->err = "null dual block"; return -2; }
+  if ((uintptr_t)d_lam & 7u) { h->err = "float64 arrays must be 8-byte aligned"; return -2; }
+  DeviceGuard guard(h->cfg.device);
+  return solve_io(h, d_xref, nullptr, nullptr, d_X, d_U, d_status, d_iters, B, (cudaStream_t)stream, 0, d_lam);
+}
+
+int32_t mpcb200_lam_words(const mpcb200_handle* h) { return h ? 14 * h->cfg.N + 2 : 0; }
 
 int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters,
                        int32_t B, void* stream) {

@@ -387,6 +387,24 @@ struct WarpSolver {
       w.sync();
     }
   }
+  // Dual block of one problem in the caller's float64 layout (include/mpcb200.h, mpcb200_solve_dual): [N][14] = the 11
+  // inequality multipliers of a stage (slot order V_DD_LO ... V_OB2) followed by its 3 obstacle slacks, then mu at exit and a
+  // validity word.  lane = ELEMENT: coalesced, every byte touched once.  R_V (11) and R_S (3) are adjacent in the stage record.
+  MPC_HD static int lam_words(int N) { return 14 * N + 2; }
+  MPC_HD bool duals_valid(const double* lam) const { return lam[14 * P.N + 1] == 1.0; }
+  MPC_HD void load_duals(const double* lam) const {
+    const int N = P.N;
+    for (int e = lane; e < 14 * N; e += 32) { const int k = e / 14, j = e - 14 * k; rc(k, R_V + j) = (T)lam[e]; }
+    w.sync();
+  }
+  MPC_HD void store_duals(double* lam, T mu) const {
+    const int N = P.N;
+    w.sync();
+    for (int e = lane; e < 14 * N; e += 32) { const int k = e / 14, j = e - 14 * k; lam[e] = (double)rc(k, R_V + j); }
+    if (lane == 0) { lam[14 * N] = (double)mu; lam[14 * N + 1] = 1.0; }
+    w.sync();
+  }
+
   // New parameter block for a slab that keeps the previous MPC step's solution (controls, slacks, multipliers): only the
   // reference-derived words and the pinned stage are rewritten.
   MPC_HD void load_reference(const double* xref, const double* obstacle_abs, T* obs_out) const {

@@ -239,6 +239,25 @@ class B200Optimizer(_Base):
         h.check(fn(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), B, self._stream()))
         return U, X, status, iters
 
+    def solve_batch_dual(self, xref, X_init, U_init, lam=None):
+        """`solve_batch` with the inequality multipliers / obstacle slacks in and out (`mpcb200_solve_dual`).  lam: CUDA tensor
+        [B, lam_words] from a previous call (warm duals) or None (cold duals; a fresh block is returned).
+        Returns (U, X, status, iters, lam)."""
+        t = self.torch
+        xref = self._dev(xref)
+        B = xref.shape[0]
+        X = self._dev(X_init).clone()
+        U = self._dev(U_init).clone()
+        h = self.handle
+        if lam is None:
+            lam = t.zeros(B, int(h.lib.mpcb200_lam_words(h.h)), dtype=t.float64, device=self.device)
+        assert lam.is_contiguous() and lam.dtype == t.float64 and lam.shape == (B, int(h.lib.mpcb200_lam_words(h.h)))
+        status = t.empty(B, dtype=t.int32, device=self.device)
+        iters = t.empty(B, dtype=t.int32, device=self.device)
+        h.check(h.lib.mpcb200_solve_dual(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), lam.data_ptr(), status.data_ptr(),
+                                         iters.data_ptr(), B, self._stream()))
+        return U, X, status, iters, lam
+
     def solve_batch_stepwise(self, xref, X_init=None, U_init=None, n_iter=None):
         """Same solve with one kernel launch per SQP iteration (KKT slab staged HBM<->smem by TMA each launch)."""
         t = self.torch

@@ -19,6 +19,7 @@ struct Job {
   ParamsT<T> P;
   T* slab;
   const double* xref; double* X; double* U;
+  double* lam;          // dual block in / out (mpcb200_solve_dual), or null
   HostWarp* hw;
   int status, iters, nsoc, trace;
   double kkt;
@@ -32,7 +33,7 @@ static void lane_body(int lane, void* arg) {
   WarpSolver<T> S(J.P, SlabRef<T>{J.slab, 0}, obs, w);
   S.load(J.xref, J.X, J.U, J.cfg->obstacle, obs);
   ProbState<T> st;
-  S.init(st);
+  if (J.lam && S.duals_valid(J.lam)) { S.load_duals(J.lam); S.init_warm(st); } else S.init(st);
   for (int it = 0; it < J.cfg->max_iter && !st.done; ++it) {
     S.iterate(st);
     if ((J.trace == 1 || J.trace == 2) && lane == 0)
@@ -40,12 +41,13 @@ static void lane_body(int lane, void* arg) {
              (double)st.kkt, (double)st.rho, (double)st.d_al, (double)st.d_ap, (double)st.d_ad, (double)st.d_c1, (double)st.d_dphi, st.d_blk / 16, st.d_blk % 16, st.status);
   }
   S.store(J.xref, J.X, J.U);
+  if (J.lam) S.store_duals(J.lam, st.mu);
   if (lane == 0) { J.status = st.status; J.iters = st.iters; J.kkt = (double)st.kkt; J.nsoc = st.nsoc; }
 }
 
 template <typename T>
 static void run(const mpcb200_config& cfg, const double* xref, double* Xio, double* Uio, int* status, int* iters,
-                double* kkt, int B, int trace) {
+                double* kkt, int B, int trace, double* lam = nullptr) {
   const int N = cfg.N;
   WLayout L(N);
   std::vector<T> buf(L.words + REC_STRIDE + 4);   // + one record: the forward sweep prefetches one record past the end
@@ -54,6 +56,7 @@ static void run(const mpcb200_config& cfg, const double* xref, double* Xio, doub
     Job<T> J;
     J.cfg = &cfg; J.P = params_from_config<T>(cfg); J.slab = buf.data();
     J.xref = xref + (size_t)b * 5 * (N + 1); J.X = Xio + (size_t)b * 5 * (N + 1); J.U = Uio + (size_t)b * 2 * N;
+    J.lam = lam ? lam + (size_t)b * (14 * N + 2) : nullptr;
     J.hw = &hw; J.trace = trace; J.status = 0; J.iters = 0; J.kkt = 0; J.nsoc = 0;
     for (auto& v : buf) v = T(NAN);        // catch reads of never-written slab words
     hw.run(&lane_body<T>, &J);
@@ -99,6 +102,11 @@ static void run_loop(const mpcb200_config& cfg, const LoopData& d) {
 }
 
 extern "C" {
+int hostsim_solve_dual(const mpcb200_config* cfg, const double* xref, double* X, double* U, double* lam, int* status, int* iters, int B) {
+  if (cfg->precision == MPCB200_F64) run<double>(*cfg, xref, X, U, status, iters, nullptr, B, 0, lam);
+  else run<float>(*cfg, xref, X, U, status, iters, nullptr, B, 0, lam);
+  return 0;
+}
 int hostsim_closed_loop(const mpcb200_config* cfg, int iter_length, const double* path, const double* orient, double vdes, const double* x0,
                         double* traj, double* ctrl, int* status, int* iters, int B) {
   LoopData d;

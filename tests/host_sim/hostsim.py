@@ -92,3 +92,17 @@ def forces_eval(consts, z, p):
     q = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     lib().hostsim_forces_eval(q(consts), q(z), q(p), q(out), n)
     return unpack_forces(out)
+
+
+def solve_dual(cfg, xref, X, U, lam=None):
+    """`mpcb200_solve_dual` on the emulator: returns (X, U, status, iters, lam [B, 14N+2])."""
+    xref = np.ascontiguousarray(xref, np.float64)
+    X = np.ascontiguousarray(X, np.float64).copy()
+    U = np.ascontiguousarray(U, np.float64).copy()
+    B, N = xref.shape[0], cfg.N
+    lam = np.zeros((B, 14 * N + 2)) if lam is None else np.ascontiguousarray(lam, np.float64).copy()
+    st = np.zeros(B, np.int32)
+    it = np.zeros(B, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().hostsim_solve_dual(C.byref(cfg), p(xref), p(X), p(U), p(lam), p(st), p(it), B)
+    return X, U, st, it, lam

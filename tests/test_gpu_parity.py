@@ -366,7 +366,7 @@ def test_recorded_ipopt_controls_pin_the_gpu_optimum_statistically(key, name, si
     from oracle import ipm, nlp
     g = np.load(os.path.join(G, "recorded_runs.npz"))
     N = 10
-    sc, opt = _opt(name, N, "f32", max_batch=64, refine_f64=1)
+    sc, opt = _opt(name, N, "f32", max_batch=128, refine_f64=1)
     Xr, Ur = g[key + "_x"], g[key + "_u"]
     T = sc.iter_length
     xref = np.stack([np.tile(x, (N + 1, 1)) if i == 0 else
@@ -581,3 +581,100 @@ def test_config5_scenarios_512_instances_each_against_the_oracle(name):
         assert np.abs(Uo - U[b]).max() < 1e-3 and np.abs(Xo - X[b]).max() < 1e-3, b
         n_cmp += 1
     assert n_cmp >= 0.9 * B
+
+
+def test_dual_block_abi_warm_start_and_mpc_step_shift():
+    """`mpcb200_solve_dual` (SURVEY 8b `d_lam`): multipliers / obstacle slacks out of one solve, in to the next.  (i) Same problem
+    again from its own solution + duals: same point, far fewer iterations than cold.  (ii) A zero block = cold duals = the
+    plain solve, bit for bit.  (iii) Through the emulator: the device code of this path equals tests/host_sim."""
+    import hostsim
+    import mpc_b200
+    from test_host_logic import _cfg
+    name, N, B = "USA_Lanker-2_18_T-1_LF", 50, 64
+    sc, opt = _opt(name, N, "f32", max_batch=B, max_iter=200)
+    _, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 31)
+    Ua, Xa, sta, ita = _np(*opt.solve_batch(xref, X0, U0))
+    Ub, Xb, stb, itb, lam = opt.solve_batch_dual(xref, X0, U0)
+    Ub, Xb, stb, itb = _np(Ub, Xb, stb, itb)
+    assert np.array_equal(Ua, Ub) and np.array_equal(Xa, Xb) and np.array_equal(ita, itb)
+    lam_h = lam.cpu().numpy()
+    assert lam_h.shape == (B, 14 * N + 2) and (lam_h[:, -1] == 1.0).all() and (lam_h[:, :-2] >= 0).all()
+    Uc, Xc, stc, itc, lam2 = opt.solve_batch_dual(xref, Xb, Ub, lam.clone())
+    Uc, Xc, stc, itc = _np(Uc, Xc, stc, itc)
+    ok = (stb == 1) & (stc == 1)
+    assert ok.mean() > 0.95 and np.abs(Uc - Ub)[ok].max() < 1e-3 and np.abs(Xc - Xb)[ok].max() < 1e-3
+    assert itc[ok].mean() < 0.6 * itb[ok].mean()
+    Xe, Ue, ste, ite, lame = hostsim.solve_dual(_cfg(sc, N, 0, max_iter=200), xref[:4], Xb[:4], Ub[:4], lam_h[:4])
+    assert np.array_equal(ite, itc[:4]) and np.abs(Ue - Uc[:4]).max() < 1e-5          # emulator = device (up to libm ulps)
+
+
+def test_closed_loop_float32_status_breakdown_config1b():
+    """the float32 closed loop of BASELINE configs[0] (ZAM_Over-1_1, N = T = 30) over 1024 perturbed egos.
+    Every MPC step ends in one of three ways: 1 (converged); -8 for egos whose perturbed initial state violates the friction row
+    (v0^2 tan(delta0) / 2.578 >= a_max: infeasible for IPOPT too) -- flagged at step 0 and, the controls being zero, at every later
+    step; 3 = stalled at the float32 rounding floor (a handful of late braking steps with v >= 0 active on several stages)."""
+    import mpc_b200
+    N, B = 30, 1024
+    sc, opt = _opt("ZAM_Over-1_1_LF", N, "f32", max_batch=B, max_iter=200)
+    x0 = mpc_b200.make_batch("ZAM_Over-1_1_LF", B, N, 7)[1]
+    tr, ct, st, it = opt.optimize_batch(x0)
+    assert np.isin(st, (1, 3, -8)).all(), np.unique(st, return_counts=True)
+    s0 = x0[:, 3] ** 2 * np.tan(x0[:, 2]) / 2.578
+    infeasible = np.abs(s0) >= 11.5
+    assert np.array_equal(st[:, 0] == -8, infeasible)
+    assert (st[infeasible] == -8).all() and (st[~infeasible] != -8).all()
+    assert (st == 3).sum() <= 0.001 * st.size
+    # the float64 loop converges every feasible step
+    sc, opt64 = _opt("ZAM_Over-1_1_LF", N, "f64", max_batch=B, max_iter=200)
+    st64 = opt64.optimize_batch(x0[:128])[2]
+    assert (st64[~infeasible[:128]] == 1).all()
+
+
+def test_noised_reference_contract_run_quirk_q9():
+    """`noised: True` (optimizer.py:611-617, quirk Q9): N(0, sigma^2) on the WHOLE control horizon, exactly 20 = 2 x 10 samples, so
+    N must be 10; the plant steps with the noisy u0.  Seeded numpy RNG -> reproducible; the applied controls differ from the
+    noise-free run by noise of the stated spread; the plant model still holds exactly between recorded states."""
+    import mpc_b200
+    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
+    from oracle import nlp
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    mk = lambda N, noised: B200Optimizer(make_configuration(sc, N, noised=noised), init_values_from_state(sc.x0), N, precision="f64", max_batch=8)   # noqa: E731
+    x0_, u0_, _ = mk(10, False).optimize()
+    np.random.seed(5)
+    x1, u1, t1 = mk(10, True).optimize()
+    np.random.seed(5)
+    x2, u2, _ = mk(10, True).optimize()
+    assert np.array_equal(x1, x2) and np.array_equal(u1, u2) and x1.shape == (30, 5) and t1.shape == (30,)
+    assert np.abs(nlp.euler_step(x1[:-1], u1[:-1], sc.dt) - x1[1:]).max() < 1e-12       # plant = Euler step with the NOISY control
+    d = u1 - u0_
+    assert 0.03 < d[:5].std() < 0.3 and np.abs(d).max() < 2.0                            # sigma = 0.1 (lane following), then the loops diverge
+    with pytest.raises(ValueError):
+        mk(30, True).optimize()                                                          # 20 samples only fit N = 10
+
+
+def test_long_horizon_n128_synthetic_straight_road():
+    """The largest horizon the library accepts (N = 128): a straight road at constant speed, perturbed starts; against the oracle."""
+    from types import SimpleNamespace
+    import mpc_b200
+    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
+    from oracle import nlp, ipm
+    base = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    N, B, v = 128, 9, 10.0
+    path = np.stack([np.arange(N + 1) * v * base.dt, np.zeros(N + 1)], axis=1)
+    sc = SimpleNamespace(**{**vars(base), "reference_path": path, "orientation": np.zeros(N + 1), "desired_velocity": v,
+                            "iter_length": N + 1, "x0": np.array([0.0, 0.0, 0.0, v, 0.0])})
+    rng = np.random.default_rng(1)
+    x0 = sc.x0[None] + rng.normal(size=(B, 5)) * np.array([0.5, 0.3, 0.01, 1.0, 0.05])
+    xref = mpc_b200.reference_window(0, x0, N, N + 1, path, sc.orientation, v)
+    for prec, tol in (("f32", 1e-3), ("f64", 1e-6)):
+        opt = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, precision=prec, max_batch=16, max_iter=200)
+        U, X, st, it = _np(*opt.solve_batch(xref))
+        assert (st == 1).all(), (prec, st, it)
+        for b in (0, B - 1):
+            d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+            r = ipm.solve(d, nlp.pack(np.zeros((N, 2)), np.tile(xref[b, 0], (N + 1, 1))))
+            assert r["status"] == 1
+            Uo, Xo = nlp.split(r["w"], N)
+            assert np.abs(U[b] - Uo).max() < tol and np.abs(X[b] - Xo).max() < tol
+    with pytest.raises(Exception):
+        B200Optimizer(make_configuration(sc, 129), init_values_from_state(sc.x0), 129, max_batch=4)      # N > 128 is rejected at create

@@ -154,3 +154,22 @@ def test_shard_ranges_cover_batch():
             r = [shard_range(B, k, W) for k in range(W)]
             assert r[0][0] == 0 and r[-1][1] == B and all(r[k][1] == r[k + 1][0] for k in range(W - 1))
             assert sum(shard_sizes(B, W)) == B and max(shard_sizes(B, W)) - min(shard_sizes(B, W)) <= 1
+
+
+@pytest.mark.parametrize("name,N", [("ZAM_Over-1_1_LF", 30), ("USA_Lanker-2_18_T-1_LF", 50), ("ZAM_Over-1_1_CA", 30)])
+def test_dual_block_round_trip_warm_starts_the_solve(name, N):
+    """`mpcb200_solve_dual` semantics on the emulator: the dual block written by a solve (multipliers, obstacle slacks, mu, valid
+    flag) re-imported together with the primal solution restarts the barrier at mu_warm and converges to the same point in a
+    few iterations; an invalid (zero) block means cold duals = the plain solve."""
+    B = 6
+    sc, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 123)
+    cfg = _cfg(sc, N, 1, max_iter=200)
+    Xa, Ua, sta, ita, _ = hostsim.solve(cfg, xref, X0, U0)
+    Xb, Ub, stb, itb, lam = hostsim.solve_dual(cfg, xref, X0, U0)
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub) and np.array_equal(ita, itb)          # zero block = cold duals
+    ok = stb == 1
+    assert ok.sum() >= B - 1 and (lam[ok, -1] == 1.0).all() and (lam[ok, :-2] >= 0).all() and (lam[ok, -2] <= cfg.mu_min * 1.01).all()
+    Xc, Uc, stc, itc, lam2 = hostsim.solve_dual(cfg, xref, Xb, Ub, lam)
+    assert (stc[ok] == 1).all()
+    assert np.abs(Uc - Ub)[ok].max() < 1e-5 and np.abs(Xc - Xb)[ok].max() < 1e-5
+    assert itc[ok].mean() <= 9.0 and (itc[ok] < itb[ok]).all()          # float64: mu_warm = 1e-4 -> 1e-9 alone takes ~5 reductions
