@@ -419,7 +419,7 @@ def run_product(args):
             dist.barrier()
             s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s_.record(wl.stream)
-            res = sharding.solve_sharded_nccl(opt, g_xref, Bg, N, src=0)
+            res = sharding.solve_sharded_nccl(opt, g_xref, Bg, N, src=0, algo=args.shard_algo)
             e_.record(wl.stream)
             if i >= 3:
                 ev2.append((s_, e_))
@@ -433,7 +433,10 @@ def run_product(args):
             ok_all = bool((stsh == 1).all().item()) and bool(torch.equal(Ush[:B], wl.d_U)) and bool(torch.equal(Ush[-B:], wl.d_U))
         nxb, nub = 5 * (N + 1) * 8, 2 * N * 8
         sharded = {"value": Bg * 1e3 / sh_ms, "unit": "solves/s", "ms_per_step": sh_ms, "global_batch": Bg, "steps": sh_steps,
-                   "collective": "NCCL scatter of xref shards from rank 0, NCCL gather of (U*, X*, status, iters) to rank 0 (torch.distributed)",
+                   "collective": ("NCCL broadcast of the parameter block from rank 0 (each rank slices its shard), NCCL all-gather of U*, X*, status, iters"
+                                  if args.shard_algo == "collective" else
+                                  "grouped NCCL send/recv: xref shards from rank 0, (U*, X*, status, iters) back to rank 0"),
+                   "algo": args.shard_algo,
                    "scatter_bytes_per_step": (world - 1) * B * nxb, "gather_bytes_per_step": (world - 1) * B * (nxb + nub + 8),
                    "collective_us_per_step": 1e3 * sh_ms - 1e3 * total_ms / steps,
                    "gathered_equals_single_gpu_solve_bitwise": ok_all,
@@ -532,6 +535,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--hessian", default="gn", choices=["exact", "gn"])
     ap.add_argument("--batch", type=int, default=BATCH, help="experiments only: batch of the headline workload (the metric is quoted at 1024)")
+    ap.add_argument("--shard-algo", default="collective", choices=["collective", "p2p"], help="NCCL data path of the `sharded` mode (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other single-GPU operating points")
     ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments; default: none)")

@@ -25,14 +25,19 @@ def main():
         sc, x0, xref, X0, U0 = mpc_b200.make_batch(name, B, N, 4242)
         opt = B200Optimizer(make_configuration(sc, N), init_values_from_state(sc.x0), N, max_batch=B, device=local, max_iter=300)
         g = torch.as_tensor(xref, device=opt.device) if rank == 0 else None
-        res = sharding.solve_sharded_nccl(opt, g, B, N, src=0)
-        torch.cuda.synchronize()
-        if rank == 0:
-            U, X, st, it = res
-            U1, X1, st1, it1 = opt.solve_batch(g)
-            same = bool(torch.equal(U, U1) and torch.equal(X, X1) and torch.equal(st, st1) and torch.equal(it, it1))
-            print(f"{name} N={N} B={B} world={world}: gathered == single-GPU solve bitwise: {same}; converged {(st == 1).sum().item()}/{B}", flush=True)
-            ok = ok and same and bool((st == 1).all().item())
+        for algo in ("collective", "p2p"):
+            res = sharding.solve_sharded_nccl(opt, g, B, N, src=0, algo=algo)
+            torch.cuda.synchronize()
+            if algo == "collective":                       # results on every rank: they must all agree with rank 0's
+                chk = res[0].sum() + res[1].sum()
+                ref = chk.clone(); dist.broadcast(ref, src=0)
+                ok = ok and bool(torch.equal(chk, ref))
+            if rank == 0:
+                U, X, st, it = res
+                U1, X1, st1, it1 = opt.solve_batch(g)
+                same = bool(torch.equal(U, U1) and torch.equal(X, X1) and torch.equal(st, st1) and torch.equal(it, it1))
+                print(f"{name} N={N} B={B} world={world} {algo}: gathered == single-GPU solve bitwise: {same}; converged {(st == 1).sum().item()}/{B}", flush=True)
+                ok = ok and same and bool((st == 1).all().item())
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

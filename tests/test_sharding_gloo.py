@@ -33,6 +33,20 @@ WORKER = textwrap.dedent("""
     arrs = {"path": np.arange(10.0).reshape(5, 2) * (1 if rank == 0 else -1), "w": np.ones(3) * (rank + 1)}
     out = broadcast_scenario(arrs)
     assert np.array_equal(out["path"], np.arange(10.0).reshape(5, 2)) and np.array_equal(out["w"], np.ones(3))
+    # the hardware data path (solve_sharded_nccl, algo="collective": broadcast + all-gather) with a stand-in optimizer on CPU tensors
+    from mpc_b200.sharding import solve_sharded_nccl
+    class FakeOpt:
+        device = torch.device("cpu")
+        def solve_batch(self, xr, out=None):
+            U, X, st, it = out
+            U.copy_(xr[:, :N, :2] * 3); X.copy_(xr + 1); st.fill_(1); it.copy_(torch.arange(xr.shape[0], dtype=torch.int32) + 100 * rank)
+            return out
+    for Bt in (37, 40):
+        xg = torch.randn(Bt, N + 1, 5, generator=torch.Generator().manual_seed(9), dtype=torch.float64)
+        U, X, st, it = solve_sharded_nccl(FakeOpt(), xg if rank == 0 else None, Bt, N, src=0, algo="collective")
+        assert U.shape == (Bt, N, 2) and torch.equal(U, xg[:, :N, :2] * 3) and torch.equal(X, xg + 1) and bool((st == 1).all())
+        exp_it = torch.cat([torch.arange(shard_range(Bt, r, world)[1] - shard_range(Bt, r, world)[0], dtype=torch.int32) + 100 * r for r in range(world)])
+        assert torch.equal(it, exp_it)
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")

@@ -64,6 +64,26 @@ def main():
             ms, n_ok, it_sum, it_max = float(mx[0]), float(sm[1]), float(sm[2]), float(mx[3])
         else:
             ms, n_ok, it_sum, it_max = [float(v) for v in stats[:4]]
+        # the same batch through the NCCL data path: rank 0 owns it, shards go out and solutions come back inside the timed region
+        sharded = None
+        if dist:
+            from mpc_b200 import sharding
+            g_xref = opt._dev(xref) if rank == 0 else None
+            for _ in range(2):
+                sharding.solve_sharded_nccl(opt, g_xref, B, N, src=0)
+            torch.cuda.synchronize(dev); dist.barrier()
+            e0.record(stream)
+            for _ in range(steps):
+                res = sharding.solve_sharded_nccl(opt, g_xref, B, N, src=0)
+            e1.record(stream); torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nxb, nub = 5 * (N + 1) * 8, 2 * N * 8
+            sharded = dict(ms_per_batch=float(t), solves_per_s=B / (float(t) * 1e-3), algo="collective (broadcast + all-gather)",
+                           scatter_bytes=(B - (hi - lo)) * nxb if rank == 0 else None,
+                           gather_bytes=(B - (hi - lo)) * (nxb + nub + 8) if rank == 0 else None)
+            if rank == 0:
+                sharded["all_converged"] = bool((res[2] == 1).all().item())
         # parity sample on rank 0's shard (oracle = checker)
         worst, n_cmp, kkt = 0.0, 0, []
         if rank == 0:
@@ -82,7 +102,7 @@ def main():
                 worst = max(worst, float(np.abs(Un[b] - Uo).max()), float(np.abs(Xn[b] - Xo).max())); n_cmp += 1
         return dict(scenario=name, B=B, N=N, gpus=world, precision=precision, ms_per_batch=ms, solves_per_s=B / (ms * 1e-3),
                     converged=f"{int(n_ok)}/{B}", mean_sqp_iters=it_sum / B, max_sqp_iters=int(it_max),
-                    parity_sample=dict(n=n_cmp, max_abs_err_vs_oracle=worst))
+                    parity_sample=dict(n=n_cmp, max_abs_err_vs_oracle=worst), **({"sharded_nccl": sharded} if sharded else {}))
 
     out = []
     # ---- config 1: reference plumbing, single ego, closed loop T = 30, N = 30 (rank 0 only)
