@@ -151,6 +151,22 @@ int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_
 int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_X, const double* h_U,
                        double* h_X_out, double* h_U_out, int32_t* h_status, int32_t* h_iters, int32_t B);
 
+/* Per-problem scenarios (SURVEY 8b `optimize_batch(x0, scenario_id[B])`, BASELINE configs[4]): one launch over problems that belong
+ * to different scenarios.  A row of the table holds what `Optimizer.__init__` takes from a scenario's `configuration`
+ * (optimizer.py:51-68): time step, weights, obstacle circles and r_ego + r_obs; bounds, horizon and solver options stay the
+ * handle's.  `mpcb200_set_scenarios` copies `n` rows (HOST pointer) to the device; `mpcb200_solve_scenarios` is
+ * `mpcb200_solve_cold` with the constants of problem b taken from row d_scenario_id[b] (device int32 [B]; ids are clamped to
+ * the table).  Gauss-Newton Hessian only.  A float32 handle with refine_f64 runs the float64 refinement pass as well. */
+typedef struct mpcb200_scenario {
+  double dt;             /* configuration.delta_t */
+  double Q[5], R[2];     /* weights_setting, order as in mpcb200_config */
+  double r_sum;          /* radius_ego + radius_obstacle */
+  double obstacle[6];    /* obstacle circle centres: centre, front, rear */
+} mpcb200_scenario;
+int mpcb200_set_scenarios(mpcb200_handle* h, const mpcb200_scenario* table, int32_t n);
+int mpcb200_solve_scenarios(mpcb200_handle* h, const double* d_xref, const int32_t* d_scenario_id, double* d_X, double* d_U,
+                            int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
+
 /* Stage functions of the reference's FORCESPRO formulation and their first derivatives -- the linearisation one SQP stage on that
  * formulation needs (ForcesproOptimizer: RK4 dynamics optimizer.py:90-98, friction circle + nine squared circle distances
  * :119-155, stage / terminal least-squares objective :163-195).  Replaces the generated model callbacks the FORCESPRO solver

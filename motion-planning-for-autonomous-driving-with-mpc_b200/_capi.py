@@ -34,6 +34,11 @@ class Config(C.Structure):
                  ("warm_duals", C.c_int32), ("warps_per_cta", C.c_int32), ("host_route", C.c_int32), ("host_chunks", C.c_int32)])
 
 
+class Scenario(C.Structure):
+    """mpcb200_scenario"""
+    _fields_ = [("dt", C.c_double), ("Q", C.c_double * 5), ("R", C.c_double * 2), ("r_sum", C.c_double), ("obstacle", C.c_double * 6)]
+
+
 EXPORTS = {
     "mpcb200_default_config": (None, [C.POINTER(Config), C.c_int32, C.c_int32]),
     "mpcb200_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -52,6 +57,8 @@ EXPORTS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_solve_cold": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_void_p]),
     "mpcb200_solve_host": (C.c_int, [C.c_void_p] * 8 + [C.c_int32]),
+    "mpcb200_set_scenarios": (C.c_int, [C.c_void_p, C.POINTER(Scenario), C.c_int32]),
+    "mpcb200_solve_scenarios": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
     "mpcb200_forces_stage_eval": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_launch_count": (C.c_int64, [C.c_void_p]),
     "mpcb200_workspace_words": (C.c_int32, [C.c_void_p]),

@@ -250,6 +250,89 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
   }
 }
 
+// ===================================================================================================== per-problem scenarios
+// BASELINE configs[4] ("all scenarios x random inits"): ONE launch over problems that belong to DIFFERENT scenarios -- weights,
+// time step and obstacle come from a device table indexed by the problem's scenario id instead of the launch constants.  A
+// separate (Gauss-Newton, cold start, fused) kernel so that the single-scenario kernel keeps its constants in the constant bank:
+// here the warp keeps the problem's ParamsT in shared memory and the solver core reads it from there.
+template <typename T>
+struct ScnArgs {
+  ParamsT<T> P;                     // everything that is not per scenario (bounds, solver options, N)
+  const mpcb200_scenario* table;    // [n_scn] device copy of the scenario table
+  const int* scn_id;                // [B]
+  const double* xref; double* X; double* U;
+  int* status; int* iters;
+  WorkCtr* ctr; int* q_list;
+  int B, n_scn, refine, dynamic, pdl_primary;
+};
+
+template <typename T, int WPC>
+__global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve_scenarios_kernel(const __grid_constant__ ScnArgs<T> a) {
+  unsigned char* const smem_raw = mpc_dyn_smem;
+  __shared__ __align__(8) uint64_t bar_x[WPC];
+  __shared__ ParamsT<T> sp[WPC];
+  __shared__ double sobst[WPC][6];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.P.N;
+  const WLayout L(N, rec_stride_for(HESS_GN));
+  const Smem<T, WPC> sm(smem_raw, N, L.words);
+  const int nx = sm.nx, nu = sm.nu;
+  const int total_warps = gridDim.x * WPC;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < WPC; ++i) mbar_init(&bar_x[i], 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (a.pdl_primary) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.refine) asm volatile("griddepcontrol.wait;" ::: "memory");
+  const WarpCtx w;
+  T obs[6];
+  const int nwork = a.refine ? a.ctr->q_count : a.B;
+  uint32_t ph_x = 0;
+  for (int item = blockIdx.x * WPC + wid; item < nwork;) {
+    const int b = a.refine ? a.q_list[item] : item;
+    // this problem's constants: launch-wide ones + its scenario's row of the table
+    __syncwarp();
+    if (lane == 0) {
+      int sid = a.scn_id[b];
+      sid = sid < 0 ? 0 : (sid >= a.n_scn ? a.n_scn - 1 : sid);
+      const mpcb200_scenario& sc = a.table[sid];
+      ParamsT<T> p = a.P;
+      p.dt = (T)sc.dt; p.r_sum = (T)sc.r_sum;
+      for (int i = 0; i < 5; ++i) p.Q[i] = (T)sc.Q[i];
+      p.R[0] = (T)sc.R[0]; p.R[1] = (T)sc.R[1];
+      sp[wid] = p;
+      for (int i = 0; i < 6; ++i) sobst[wid][i] = sc.obstacle[i];
+    }
+    __syncwarp();
+    WarpSolver<T, HESS_GN> S(sp[wid], SlabRef<T>{wid * L.words}, obs, w);
+    ProbState<T> st;
+    const double* xr = fetch_xref(a.xref + (size_t)b * nx, sm.xstg(wid), nx, &bar_x[wid], ph_x, lane);
+    if (a.refine) S.load(xr, a.X + (size_t)b * nx, a.U + (size_t)b * nu, sobst[wid], obs);      // warm start = the float32 result
+    else S.load(xr, nullptr, nullptr, sobst[wid], obs);
+    S.init(st);
+    for (int it = 0; it < a.P.max_iter && !st.done; ++it) S.iterate(st);
+    S.store(xr, a.X + (size_t)b * nx, a.U + (size_t)b * nu);
+    if (lane == 0) {
+      if (a.status) a.status[b] = st.status;
+      if (a.iters) a.iters[b] = st.iters + (a.refine ? a.iters[b] : 0);
+      if (a.q_list && !a.refine && st.status != ST_OPTIMAL && st.status != ST_INFEASIBLE_X0) a.q_list[atomicAdd(&a.ctr->q_count, 1)] = b;
+    }
+    if (!a.dynamic) break;
+    int nxt = 0;
+    if (lane == 0) nxt = total_warps + atomicAdd(&a.ctr->next, 1);
+    item = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+  if ((a.dynamic || a.refine) && lane == 0 && !(a.refine && nwork == 0)) {
+    __threadfence();
+    if (atomicAdd(&a.ctr->done, 1) == total_warps - 1) {
+      a.ctr->next = 0; a.ctr->done = 0;
+      if (a.refine) a.ctr->q_count = 0;
+    }
+  }
+}
+
 // ===================================================================================================== closed loop
 // The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631), one ego per warp, no host round trip
 // between MPC steps (loop body: loop_core.cuh).  Persistent warps like the solve kernel.  Shared memory per warp: the KKT slab
@@ -352,6 +435,9 @@ struct mpcb200_handle {
   void* obs_shift;
   WorkCtr* ctr;         // device work counters (zeroed at create, self-resetting afterwards)
   int* q_list;          // [max_batch] refinement queue (refine_f64 handles)
+  mpcb200_scenario* scn_table;   // device copy of the scenario table (mpcb200_set_scenarios)
+  int n_scn;
+  KernelPlan scn, scn_refine;    // launch shapes of the per-problem-scenario kernels (planned at set_scenarios)
   size_t elem;          // sizeof(T)
   int64_t launches;
   // stepwise-mode context
@@ -552,6 +638,39 @@ static cudaError_t closed_loop_t(mpcb200_handle* h, int32_t iter_length, const d
   return dispatch_loop<T>(h, a, s);
 }
 
+template <typename T>
+static cudaError_t plan_scn(KernelPlan& k, int optin, int sms) {
+  cudaError_t e = cudaSuccess;
+  switch (k.wpc) {
+    case 2: e = plan_kernel(mpc_warp_solve_scenarios_kernel<T, 2>, 2, k.smem, optin, sms, &k.max_ctas); break;
+    default: k.wpc = 1; e = plan_kernel(mpc_warp_solve_scenarios_kernel<T, 1>, 1, k.smem, optin, sms, &k.max_ctas); break;
+  }
+  return e;
+}
+template <typename T>
+static cudaError_t launch_scn(mpcb200_handle* h, ScnArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
+  const int ctas = grid_for(k, nwork);
+  a.dynamic = (a.refine || nwork > ctas * k.wpc) ? 1 : 0;
+  h->launches++;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(32 * k.wpc); cfg.dynamicSmemBytes = k.smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = a.refine ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (k.wpc == 2) return cudaLaunchKernelEx(&cfg, mpc_warp_solve_scenarios_kernel<T, 2>, a);
+  return cudaLaunchKernelEx(&cfg, mpc_warp_solve_scenarios_kernel<T, 1>, a);
+}
+
+template <typename T>
+static void fill_scn_args(mpcb200_handle* h, ScnArgs<T>& a, const double* xref, const int32_t* sid, double* X, double* U, int32_t* status,
+                          int32_t* iters, int32_t B) {
+  a.P = params_from_config<T>(h->cfg);
+  a.table = h->scn_table; a.scn_id = sid; a.n_scn = h->n_scn;
+  a.xref = xref; a.X = X; a.U = U; a.status = status; a.iters = iters;
+  a.ctr = h->ctr; a.q_list = nullptr; a.B = B; a.refine = 0; a.dynamic = 0; a.pdl_primary = 0;
+}
+
 extern "C" {
 
 int32_t mpcb200_abi_version(void) { return MPCB200_ABI_VERSION; }
@@ -576,7 +695,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   h = new (std::nothrow) mpcb200_handle();
   if (!h) { g_create_err = "out of host memory"; return -4; }
   h->cfg = *cfg;
-  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr; h->ctr = nullptr; h->q_list = nullptr;
+  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr; h->ctr = nullptr; h->q_list = nullptr; h->scn_table = nullptr; h->n_scn = 0;
   h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
   h->sw_xref = nullptr; h->sw_B = 0;
   const bool exact = cfg->hessian == MPCB200_HESS_EXACT;
@@ -614,7 +733,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
 void mpcb200_destroy(mpcb200_handle* h) {
   if (!h) return;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift); cudaFree(h->ctr); cudaFree(h->q_list);
+  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift); cudaFree(h->ctr); cudaFree(h->q_list); cudaFree(h->scn_table);
   if (h->h_pin) for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) cudaStreamDestroy(h->hs[i]);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -789,6 +908,61 @@ int mpcb200_solve_host(mpcb200_handle* h, const double* h_xref, const double* h_
   for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) CK(cudaStreamSynchronize(h->hs[i]));
   if (h_status) memcpy(h_status, h->h_pin, (size_t)B * 4);
   if (h_iters) memcpy(h_iters, h->h_pin + mb, (size_t)B * 4);
+  return 0;
+}
+
+int mpcb200_set_scenarios(mpcb200_handle* h, const mpcb200_scenario* table, int32_t n) {
+  if (!h) return -2;
+  if (!table || n < 1 || n > 4096) { h->err = "scenario table: need 1 .. 4096 rows"; return -2; }
+  if (h->cfg.hessian == MPCB200_HESS_EXACT) { h->err = "per-problem scenarios are built for the Gauss-Newton Hessian only"; return -2; }
+  DeviceGuard guard(h->cfg.device);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+  const int optin = (int)prop.sharedMemPerBlockOptin, sms = prop.multiProcessorCount;
+  const bool f64 = h->cfg.precision == MPCB200_F64;
+  h->scn.wpc = h->solve.wpc == 4 ? 2 : h->solve.wpc; h->scn.smem = smem_bytes_for(h->cfg.N, h->words, h->elem, h->scn.wpc);
+  cudaError_t e = f64 ? plan_scn<double>(h->scn, optin, sms) : plan_scn<float>(h->scn, optin, sms);
+  if (e != cudaSuccess) return fail(h, "kernel configuration (per-problem scenarios)", e);
+  h->scn_refine.wpc = 0;
+  if (!f64 && h->cfg.refine_f64) {
+    h->scn_refine.wpc = 1; h->scn_refine.smem = smem_bytes_for(h->cfg.N, h->words, 8, 1);
+    e = plan_scn<double>(h->scn_refine, optin, sms);
+    if (e != cudaSuccess) return fail(h, "kernel configuration (per-problem scenarios, float64 refinement)", e);
+    if (h->scn_refine.max_ctas > sms) h->scn_refine.max_ctas = sms;
+  }
+  cudaFree(h->scn_table); h->scn_table = nullptr;
+  CK(cudaMalloc(&h->scn_table, (size_t)n * sizeof(mpcb200_scenario)));
+  CK(cudaMemcpy(h->scn_table, table, (size_t)n * sizeof(mpcb200_scenario), cudaMemcpyHostToDevice));
+  h->n_scn = n;
+  return 0;
+}
+
+int mpcb200_solve_scenarios(mpcb200_handle* h, const double* d_xref, const int32_t* d_scenario_id, double* d_X, double* d_U,
+                            int32_t* d_status, int32_t* d_iters, int32_t B, void* stream) {
+  if (!h) return -2;
+  if (B <= 0) return 0;
+  if (!h->scn_table) { h->err = "mpcb200_solve_scenarios without mpcb200_set_scenarios"; return -2; }
+  if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  if (!d_xref || !d_scenario_id || !d_X || !d_U) { h->err = "null argument"; return -2; }
+  if (((uintptr_t)d_xref | (uintptr_t)d_X | (uintptr_t)d_U) & 7u) { h->err = "float64 arrays must be 8-byte aligned"; return -2; }
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e;
+  if (h->cfg.precision == MPCB200_F64) {
+    ScnArgs<double> a; fill_scn_args(h, a, d_xref, d_scenario_id, d_X, d_U, d_status, d_iters, B);
+    e = launch_scn<double>(h, a, s, h->scn, B);
+  } else {
+    const bool refine = h->cfg.refine_f64 && d_status && h->scn_refine.wpc;
+    ScnArgs<float> a; fill_scn_args(h, a, d_xref, d_scenario_id, d_X, d_U, d_status, d_iters, B);
+    a.q_list = refine ? h->q_list : nullptr; a.pdl_primary = refine ? 1 : 0;
+    e = launch_scn<float>(h, a, s, h->scn, B);
+    if (e == cudaSuccess && refine) {
+      ScnArgs<double> r; fill_scn_args(h, r, d_xref, d_scenario_id, d_X, d_U, d_status, d_iters, B);
+      r.q_list = h->q_list; r.refine = 1;
+      e = launch_scn<double>(h, r, s, h->scn_refine, B);
+    }
+  }
+  if (e != cudaSuccess) return fail(h, "mpc_warp_solve_scenarios_kernel launch", e);
   return 0;
 }
 

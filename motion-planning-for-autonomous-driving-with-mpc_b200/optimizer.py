@@ -239,6 +239,43 @@ class B200Optimizer(_Base):
         h.check(fn(h.h, xref.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(), iters.data_ptr(), B, self._stream()))
         return U, X, status, iters
 
+    def set_scenarios(self, scenarios):
+        """Scenario table for `solve_batch_scenarios` (BASELINE configs[4]: several scenarios in ONE launch).  `scenarios`: objects
+        with the fields `Optimizer.__init__` reads from a configuration (`dt` / `delta_t`, `weights_setting`, `static_obstacle`),
+        e.g. `mpc_b200.load_scenario(...)`.  Bounds, horizon and solver options stay this optimizer's."""
+        tab = (_capi.Scenario * len(scenarios))()
+        for i, sc in enumerate(scenarios):
+            w = sc.weights_setting
+            tab[i].dt = float(getattr(sc, "dt", getattr(sc, "delta_t", self.delta_t)))
+            for j, k in enumerate(("weight_x", "weight_y", "weight_steering_angle", "weight_velocity", "weight_heading_angle")):
+                tab[i].Q[j] = float(w[k])
+            tab[i].R[0], tab[i].R[1] = float(w["weight_velocity_steering_angle"]), float(w["weight_long_acceleration"])
+            circles, r_sum, _ = obstacle_circles_and_radius(sc.static_obstacle, self.configuration.p)
+            tab[i].r_sum = float(r_sum)
+            for j in range(3):
+                tab[i].obstacle[2 * j], tab[i].obstacle[2 * j + 1] = float(circles[j][0]), float(circles[j][1])
+        h = self.handle
+        h.check(h.lib.mpcb200_set_scenarios(h.h, tab, len(scenarios)))
+        self.n_scenarios = len(scenarios)
+
+    def solve_batch_scenarios(self, xref, scenario_id):
+        """One cold-start NLP solve per row with the constants of row b taken from scenario `scenario_id[b]` of the table set by
+        `set_scenarios` (one launch for the whole mixed batch).  Returns (U, X, status, iters) like `solve_batch`."""
+        t = self.torch
+        xref = self._dev(xref)
+        B = xref.shape[0]
+        sid = t.as_tensor(np.ascontiguousarray(scenario_id, np.int32) if not isinstance(scenario_id, t.Tensor) else scenario_id,
+                          device=self.device).to(t.int32).contiguous()
+        assert sid.shape == (B,) and xref.shape[1:] == (self.N + 1, 5)
+        X = t.empty(B, self.N + 1, 5, dtype=t.float64, device=self.device)
+        U = t.empty(B, self.N, 2, dtype=t.float64, device=self.device)
+        status = t.empty(B, dtype=t.int32, device=self.device)
+        iters = t.empty(B, dtype=t.int32, device=self.device)
+        h = self.handle
+        h.check(h.lib.mpcb200_solve_scenarios(h.h, xref.data_ptr(), sid.data_ptr(), X.data_ptr(), U.data_ptr(), status.data_ptr(),
+                                              iters.data_ptr(), B, self._stream()))
+        return U, X, status, iters
+
     def solve_batch_dual(self, xref, X_init, U_init, lam=None):
         """`solve_batch` with the inequality multipliers / obstacle slacks in and out (`mpcb200_solve_dual`).  lam: CUDA tensor
         [B, lam_words] from a previous call (warm duals) or None (cold duals; a fresh block is returned).

@@ -678,3 +678,31 @@ def test_long_horizon_n128_synthetic_straight_road():
             assert np.abs(U[b] - Uo).max() < tol and np.abs(X[b] - Xo).max() < tol
     with pytest.raises(Exception):
         B200Optimizer(make_configuration(sc, 129), init_values_from_state(sc.x0), 129, max_batch=4)      # N > 128 is rejected at create
+
+
+def test_per_problem_scenarios_one_launch_equals_per_scenario_launches():
+    """BASELINE configs[4] in ONE launch: a shuffled mixed batch of all six scenarios (different weights, obstacle, and dt = 0.25 for
+    Urban-3_2) solved with per-problem scenario ids must equal, instance by instance, what each scenario's own handle returns."""
+    import mpc_b200
+    names = ["ZAM_Over-1_1_CA", "ZAM_Over-1_1_LFfile", "USA_Lanker-2_18_T-1_LF", "USA_Peach-2_1_T-1", "ZAM_Tutorial-1_2_T-1", "ZAM_Tutorial_Urban-3_2"]
+    N, per = 30, 96
+    scs, xrefs, ref = [], [], []
+    for i, name in enumerate(names):
+        sc, opt = _opt(name, N, "f32", max_batch=per, max_iter=300)
+        _, x0, xref, X0, U0 = mpc_b200.make_batch(name, per, N, 20261020 + i)
+        scs.append(sc); xrefs.append(xref); ref.append(_np(*opt.solve_batch(xref)))
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(names) * per)
+    xref_all = np.concatenate(xrefs)[perm]
+    sid = np.repeat(np.arange(len(names)), per)[perm].astype(np.int32)
+    sc0, mixed = _opt(names[1], N, "f32", max_batch=len(perm), max_iter=300, refine_f64=1)
+    mixed.set_scenarios(scs)
+    n0 = mixed.handle.launch_count
+    U, X, st, it = _np(*mixed.solve_batch_scenarios(xref_all, sid))
+    assert mixed.handle.launch_count - n0 == 2                      # the mixed float32 pass + its float64 refinement pass
+    Ur = np.concatenate([r[0] for r in ref])[perm]; Xr = np.concatenate([r[1] for r in ref])[perm]
+    str_ = np.concatenate([r[2] for r in ref])[perm]; itr = np.concatenate([r[3] for r in ref])[perm]
+    assert (st == 1).all() and np.array_equal(st, str_)
+    lf = sid != 0                                                    # lane-following scenarios: no refinement involved -> bit-identical
+    assert np.array_equal(U[lf], Ur[lf]) and np.array_equal(X[lf], Xr[lf]) and np.array_equal(it[lf], itr[lf])
+    assert np.abs(U[~lf] - Ur[~lf]).max() < 1e-3 and np.abs(X[~lf] - Xr[~lf]).max() < 1e-3
