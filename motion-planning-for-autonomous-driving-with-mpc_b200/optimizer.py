@@ -418,7 +418,8 @@ class B200Optimizer(_Base):
 
         Noise-free runs (`configuration.noised` false) execute the whole receding-horizon loop on the device in ONE launch
         (`mpcb200_closed_loop` = `optimize_batch` with B = 1); `t_v` then holds the measured loop time divided evenly over the
-        T steps (the device loop has no per-step host clock).  With `noised` (or `on_device=False`) the loop runs step by
+        T steps (the device loop has no per-step host clock).  With `noised`, with a float32 handle that needs the float64
+        refinement pass (obstacle within reach of the path), or with `on_device=False`, the loop runs step by
         step from the host in the reference's own shape -- solve -> first control (+ noise) -> plant step + shift -> next
         window -- with the solve time of each step measured like the reference does (wall clock around the solve,
         optimizer.py:603-608).  `noised` uses the reference's noise law and needs N == 10 (optimizer.py:611-615, quirk Q9)."""
@@ -428,7 +429,9 @@ class B200Optimizer(_Base):
                                self.init_orientation], float)
         noised = bool(getattr(self.configuration, "noised", False))
         if on_device is None:
-            on_device = not noised
+            # the device loop has no float64 refinement pass: a float32 handle whose obstacle is within reach (refine_f64 set)
+            # runs the loop step by step from the host instead, where every solve is followed by its refinement launch
+            on_device = not noised and not (self.cfg.precision == _capi.F32 and self.cfg.refine_f64)
         if on_device:
             if noised:
                 raise ValueError("the device loop is noise-free; use on_device=False with configuration.noised")
