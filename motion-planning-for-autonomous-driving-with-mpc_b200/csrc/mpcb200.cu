@@ -149,7 +149,10 @@ template <typename T, int WPC> struct MinBlocks { static constexpr int v = (size
 // device counter until the batch is empty -- problems need 4 ... 60 SQP iterations, so static pairing would idle a finished
 // warp until its CTA partner is done.  All SQP iterations of a problem run inside the launch (MODE_ONESHOT), or `n_iter` of
 // them with the slab round-tripping HBM <-> shared memory by TMA (stepwise modes).
-template <typename T, int WPC, int HM>
+// DUAL = 1: the instantiation behind mpcb200_solve_dual (multipliers / slacks in and out).  A separate instantiation because the
+// dual warm start (init_warm) is a second copy of the initialisation code: inlined into the plain kernel it cost 5 registers and
+// 2 % of the batch-1024 time without ever being executed there.
+template <typename T, int WPC, int HM, int DUAL>
 __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve_kernel(const __grid_constant__ SolveArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   __shared__ __align__(8) uint64_t bar_x[WPC];     // xref staging
@@ -188,9 +191,13 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
     if (need_xref) xr = fetch_xref(a.xref + (size_t)b * nx, sm.xstg(wid), nx, &bar_x[wid], ph_x, lane);
     if (need_init) {
       S.load(xr, need_warm ? a.Xin + (size_t)b * nx : nullptr, need_warm ? a.Uin + (size_t)b * nu : nullptr, a.obstacle, obs);
-      double* const lam_b = a.lam ? a.lam + (size_t)b * WarpSolver<T, HM>::lam_words(N) : nullptr;
-      if (lam_b && need_warm && !a.refine && S.duals_valid(lam_b)) { S.load_duals(lam_b); S.init_warm(st); }   // dual warm start
-      else S.init(st);
+      bool warm_duals = false;
+      if (DUAL) {
+        const double* const lam_b = a.lam + (size_t)b * WarpSolver<T, HM>::lam_words(N);
+        warm_duals = need_warm && !a.refine && S.duals_valid(lam_b);
+        if (warm_duals) { S.load_duals(lam_b); S.init_warm(st); }                                    // dual warm start
+      }
+      if (!warm_duals) S.init(st);
     } else {
       // resume: the slab image comes back by one TMA bulk copy, the per-problem scalars by plain loads
       fence_async_smem();
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(32 * WPC, MinBlocks<T, WPC>::v) mpc_warp_solve
     if (a.mode == MODE_ONESHOT || a.mode == MODE_END) {
       // solution back to float64 row-major (rho is added back in float64): coalesced stores straight from the slab
       S.store(xr, a.X + (size_t)b * nx, a.U + (size_t)b * nu);
-      if (a.lam) S.store_duals(a.lam + (size_t)b * WarpSolver<T, HM>::lam_words(N), st.mu);
+      if (DUAL) S.store_duals(a.lam + (size_t)b * WarpSolver<T, HM>::lam_words(N), st.mu);
       if (lane == 0) {
         if (a.status) a.status[b] = st.status;
         if (a.iters) a.iters[b] = st.iters + (a.refine ? a.iters[b] : 0);
@@ -487,9 +494,11 @@ static cudaError_t launch_solve(mpcb200_handle* h, SolveArgs<T>& a, cudaStream_t
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mpc_warp_solve_kernel<T, WPC, HM>, a);
+    if (a.lam) return cudaLaunchKernelEx(&cfg, mpc_warp_solve_kernel<T, WPC, HM, 1>, a);
+    return cudaLaunchKernelEx(&cfg, mpc_warp_solve_kernel<T, WPC, HM, 0>, a);
   }
-  mpc_warp_solve_kernel<T, WPC, HM><<<ctas, 32 * WPC, k.smem, s>>>(a);
+  if (a.lam) mpc_warp_solve_kernel<T, WPC, HM, 1><<<ctas, 32 * WPC, k.smem, s>>>(a);
+  else mpc_warp_solve_kernel<T, WPC, HM, 0><<<ctas, 32 * WPC, k.smem, s>>>(a);
   return cudaGetLastError();
 }
 template <typename T, int WPC, int HM>
@@ -543,8 +552,14 @@ static cudaError_t plan_kernel(K kern, int wpc, size_t smem, int optin, int sms,
 template <typename T>
 static cudaError_t plan_solve(KernelPlan& k, bool exact, int optin, int sms) {
   cudaError_t e = cudaSuccess;
-  MPC_DISPATCH_WPC(k.wpc, e = exact ? plan_kernel(mpc_warp_solve_kernel<T, W, HESS_EXACT>, W, k.smem, optin, sms, &k.max_ctas)
-                                    : plan_kernel(mpc_warp_solve_kernel<T, W, HESS_GN>, W, k.smem, optin, sms, &k.max_ctas));
+  int dual_ctas = 0;
+  MPC_DISPATCH_WPC(k.wpc, e = exact ? plan_kernel(mpc_warp_solve_kernel<T, W, HESS_EXACT, 0>, W, k.smem, optin, sms, &k.max_ctas)
+                                    : plan_kernel(mpc_warp_solve_kernel<T, W, HESS_GN, 0>, W, k.smem, optin, sms, &k.max_ctas));
+  if (e == cudaSuccess) {
+    MPC_DISPATCH_WPC(k.wpc, e = exact ? plan_kernel(mpc_warp_solve_kernel<T, W, HESS_EXACT, 1>, W, k.smem, optin, sms, &dual_ctas)
+                                      : plan_kernel(mpc_warp_solve_kernel<T, W, HESS_GN, 1>, W, k.smem, optin, sms, &dual_ctas));
+    if (e == cudaSuccess && dual_ctas < k.max_ctas) k.max_ctas = dual_ctas;      // one grid shape for both instantiations
+  }
   return e;
 }
 template <typename T>

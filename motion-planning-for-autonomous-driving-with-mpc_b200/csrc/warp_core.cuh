@@ -1055,6 +1055,7 @@ struct WarpSolver {
     nz += mu * lga;
     ok = w.all(ok);
     dphi = w.sum(dphi); c1 = w.sum(c1); nz = w.sum(nz);
+    w.sync();          // the next trial / the restored forward sweep overwrites the trial states and the step these lanes just read
     return ok;
   }
 
