@@ -152,6 +152,8 @@ struct SlabRef {
 };
 #endif
 
+template <bool B> struct FetchTag { static constexpr bool value = B; };      // compile-time "prefetch the next record" flag of the sweeps
+
 // HM: Hessian mode fixed at compile time (HESS_GN / HESS_EXACT: the kernels, so that a Gauss-Newton kernel carries no
 // exact-Hessian code between its hot phases -- instruction-cache footprint) or HESS_RUNTIME (P.hessian decides: the
 // host emulator).
@@ -701,21 +703,22 @@ struct WarpSolver {
     const T* pe0 = &sl[last + tb.e[0]]; const T* pe1 = &sl[last + tb.e[1]]; const T* pe2 = &sl[last + tb.e[2]];
     const T* pr = &sl[last + R_RU];
     T* pk = &sl[last + R_KK + tb.j];
-    // loads the record the pointers stand on, then steps them one record down -- except below record 0 (`step` = 0 there: the
-    // last prefetch re-reads record 0 instead of reading below the records; branch-free, a uniform select on the bump)
-    auto fetch = [&](BwdCoef& q, int step) {
+    // loads the record the pointers stand on, then steps them one record down (constant bump: folded into the load offsets of
+    // the two-stage loop body).  Nothing is read below record 0: the stage that would prefetch it is instantiated WITHOUT the
+    // fetch (`more` is a compile-time tag), in the loop epilogue.
+    auto fetch = [&](BwdCoef& q) {
       q.h = *ph; q.c0 = *pc0; q.c1 = *pc1; q.c2 = *pc2; q.c3 = *pc3; q.c4 = *pc4; q.e0 = *pe0; q.e1 = *pe1; q.e2 = *pe2;
       q.Ru0 = pr[0]; q.Ru1 = pr[1]; q.rp0 = pr[2]; q.rp1 = pr[3];
-      ph -= step; pc0 -= step; pc1 -= step; pc2 -= step; pc3 -= step; pc4 -= step;
-      pe0 -= step; pe1 -= step; pe2 -= step; pr -= step;
+      ph -= RS; pc0 -= RS; pc1 -= RS; pc2 -= RS; pc3 -= RS; pc4 -= RS;
+      pe0 -= RS; pe1 -= RS; pe2 -= RS; pr -= RS;
     };
-    auto stage = [&](int k, const BwdCoef& cur, BwdCoef& nxt) -> bool {
+    auto stage = [&](int k, const BwdCoef& cur, BwdCoef& nxt, auto more) -> bool {
       Pij += cur.h;                                   // x_{k+1} terms
       // round 1: control block + M = [P|p] * Atilde
       const T p22 = w.shfl(Pij, 14), p23 = w.shfl(Pij, 15), p33 = w.shfl(Pij, 21);
       const T q0 = w.shfl(Pij, tb.s1[0]), q1 = w.shfl(Pij, tb.s1[1]), q2 = w.shfl(Pij, tb.s1[2]);
       const T q3 = w.shfl(Pij, tb.s1[3]), q4 = w.shfl(Pij, tb.s1[4]);
-      fetch(nxt, k >= 2 ? RS : 0);   // record k-1, off the dependent chain (at k = 0: record 0 once more, never below the records)
+      if (decltype(more)::value) fetch(nxt);   // record k-1, off the dependent chain
       const T M = ownf * Pij + ((cur.c0 * q0 + cur.c1 * q1) + (cur.c2 * q2 + cur.c3 * q3) + cur.c4 * q4);
       // G / dt^2 (the stored control diagonal is pre-divided): J = -dt^2 G^-1 = -(G / dt^2)^-1 needs no dt^2 on the chain
       const T G00 = cur.Ru0 + p22, G01 = p23, G11 = cur.Ru1 + p33;
@@ -761,13 +764,17 @@ struct WarpSolver {
     };
     // two stages per trip with ping-pong coefficient registers (no register moves between stages)
     BwdCoef ca, cb;
-    fetch(ca, N >= 2 ? RS : 0);
+    const FetchTag<true> yes; const FetchTag<false> no;
+    fetch(ca);                                            // record N-1
     int k = N - 1;
-    for (; k >= 1; k -= 2) {
-      if (!stage(k, ca, cb)) { ok = false; break; }
-      if (!stage(k - 1, cb, ca)) { ok = false; break; }
+    for (; k >= 2; k -= 2) {                              // both stages of a trip have a record below them to prefetch
+      if (!stage(k, ca, cb, yes)) { ok = false; break; }
+      if (!stage(k - 1, cb, ca, yes)) { ok = false; break; }
     }
-    if (ok && k == 0) ok = stage(0, ca, cb);
+    if (ok) {
+      if (k == 1) ok = stage(1, ca, cb, yes) && stage(0, cb, ca, no);
+      else ok = stage(0, ca, cb, no);
+    }
     w.sync();
     return ok;
   }
@@ -792,12 +799,12 @@ struct WarpSolver {
     const T* pf3 = &sl[L.o_rec + tb.fc[3]]; const T* pf4 = &sl[L.o_rec + tb.fc[4]]; const T* pfc = &sl[L.o_rec + tb.fc0];
     T* pd = &sl[L.o_rec + row];
     const T* pl = &sl[L.o_rec + row];
-    // loads record j (where the pointers stand), then steps them up -- except past the last record (`step` = 0 there)
-    auto fetch = [&](FwdCoef& q, int step) {
+    // loads record j (where the pointers stand), then steps them up; the last stage is instantiated without the fetch
+    auto fetch = [&](FwdCoef& q) {
       q.f0 = *pf0; q.f1 = *pf1; q.f2 = *pf2; q.f3 = *pf3; q.f4 = *pf4; q.fc = *pfc; q.d = pl[R_D];
-      pf0 += step; pf1 += step; pf2 += step; pf3 += step; pf4 += step; pfc += step; pl += step;
+      pf0 += RS; pf1 += RS; pf2 += RS; pf3 += RS; pf4 += RS; pfc += RS; pl += RS;
     };
-    auto stage = [&](int k, const FwdCoef& cur, FwdCoef& nxt) {
+    auto stage = [&](const FwdCoef& cur, FwdCoef& nxt, auto more) {
       const T acc = (cur.fc + cur.f0 * dx0) + (cur.f1 * dx1 + cur.f2 * dx2) + (cur.f3 * dx3 + cur.f4 * dx4);
       const T nx = (mine + cur.d) + acc;
       dx0 = w.shfl(nx, 0); dx1 = w.shfl(nx, 1); dx2 = w.shfl(nx, 2); dx3 = w.shfl(nx, 3); dx4 = w.shfl(nx, 4);
@@ -805,13 +812,15 @@ struct WarpSolver {
       if (lane < 5) pd[R_DX] = nx;
       if (lane == 2 || lane == 3) pd[R_DU - 2] = acc * idt;
       pd += RS;
-      fetch(nxt, k + 2 < N ? RS : 0);   // record k+1 (at k = N-1: record N-1 once more, never past the last record)
+      if (decltype(more)::value) fetch(nxt);   // record k+1
     };
     FwdCoef ca, cb;
-    fetch(ca, N >= 2 ? RS : 0);
+    const FetchTag<true> yes; const FetchTag<false> no;
+    fetch(ca);                                            // record 0
     int k = 0;
-    for (; k + 1 < N; k += 2) { stage(k, ca, cb); stage(k + 1, cb, ca); }
-    if (k < N) stage(k, ca, cb);
+    for (; k + 2 < N; k += 2) { stage(ca, cb, yes); stage(cb, ca, yes); }      // stages k, k+1 with a record k+2 <= N-1 after them
+    if (k + 2 == N) { stage(ca, cb, yes); stage(cb, ca, no); }
+    else stage(ca, cb, no);
     w.sync();
   }
 
