@@ -71,7 +71,7 @@ typedef struct mpcb200_config {
   double acc_factor;               /* acceptable exit: acc_iters consecutive steps <= acc_factor * tol_step at mu_min */
   int32_t acc_iters;
   int32_t stall_iters;             /* status 3 after this many iterations at mu_min without halving the step (noise floor) */
-  int32_t refine_f64;              /* precision F32 only: re-solve instances that did not reach status 1 in float64 arithmetic (second launch) */
+  int32_t refine_f64;              /* precision F32 only (default 1): instances that did not reach status 1 are queued on the device and re-solved in float64 arithmetic by a second, persistent launch */
   int32_t init_rollout;            /* 1: initial states = Euler rollout of the initial controls from X_0 (X warm start ignored) */
   /* ---- ABI 4 */
   double mu_warm;                  /* dual warm start: barrier parameter a warm-started solve restarts at (instead of mu0) */
@@ -117,7 +117,9 @@ int mpcb200_solve_cold(mpcb200_handle* h, const double* d_xref, double* d_X, dou
 
 /* Same solve, one kernel launch per SQP iteration with the per-problem KKT slab (iterate, multipliers, slacks,
  * Riccati blocks) staged HBM -> shared memory by TMA bulk copy and written back each launch:
- *   begin: load problem data, initialise;  iter: `n_iter` iterations per call;  end: write X, U, status, iters. */
+ *   begin: load problem data, initialise;  iter: `n_iter` iterations per call;  end: write X, U, status, iters.
+ * No float64 refinement pass in this mode (cfg.refine_f64 is honoured by solve / solve_cold / solve_dual / solve_host /
+ * solve_scenarios): a float32 instance that stalls on an active obstacle row keeps status 3. */
 int mpcb200_sqp_begin(mpcb200_handle* h, const double* d_xref, const double* d_X, const double* d_U, int32_t B, void* cuda_stream);
 int mpcb200_sqp_iter(mpcb200_handle* h, int32_t n_iter, void* cuda_stream);
 int mpcb200_sqp_end(mpcb200_handle* h, double* d_X, double* d_U, int32_t* d_status, int32_t* d_iters, void* cuda_stream);
@@ -136,7 +138,11 @@ int mpcb200_build_ref_window(mpcb200_handle* h, int32_t i, int32_t iter_length, 
 /* The whole receding-horizon loop of CasadiOptimizer.optimize() (optimizer.py:596-631) on the device, no host
  * sync between MPC steps: for i in 0..iter_length-1: solve, record u_0, plant step + shift, next window.
  * d_x0 [B][5]; outputs d_traj [B][iter_length][5] (Q12: x0 first, last dropped), d_ctrl [B][iter_length][2],
- * d_status [B][iter_length], d_iters [B][iter_length] (may be NULL). */
+ * d_status [B][iter_length], d_iters [B][iter_length] (may be NULL).
+ * cfg.warm_duals = 1 carries slacks / multipliers across the MPC steps (default 0 = restart every step like IPOPT in the
+ * reference).  No float64 refinement pass inside the loop: with float32 arithmetic and an obstacle within reach, stalled steps
+ * are reported as status 3 -- use precision F64 for such closed loops (B200Optimizer.optimize() routes them through the
+ * per-step host loop, where every solve has its refinement launch). */
 int mpcb200_closed_loop(mpcb200_handle* h, int32_t iter_length, const double* d_path, const double* d_orientation,
                         double desired_velocity, const double* d_x0, double* d_traj, double* d_ctrl,
                         int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);

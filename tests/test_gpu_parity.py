@@ -546,14 +546,20 @@ def test_config4_lanker_n50_against_the_oracle_on_1024_instances():
     cores = min(os.cpu_count() or 1, 32)
     with mp.get_context("fork").Pool(cores, initializer=_one_blas_thread) as pool:
         res = pool.map(bench._oracle_one, [(name, N, xref[b], X0[b], U0[b]) for b in idx], chunksize=4)
+        # the oracle's own IPM fails from the cold start on ~15 % of these instances (Lanker weights, cost scale 1e6): those are
+        # checked the other way round -- warm-started AT the GPU point the oracle must converge and stay within the tolerance
+        failed = [b for b, r in zip(idx, res) if r[0] != 1]
+        wres = pool.map(bench._warm_one, [(name, N, xref[b], X[b], U[b]) for b in failed], chunksize=4)
     n_cmp = 0
     for b, (st_o, _, w_o) in zip(idx, res):
         if st_o != 1:
-            continue                                   # the oracle's own IPM is less robust than the device solver
+            continue
         Uo, Xo = nlp.split(w_o, N)
         assert np.abs(Uo - U[b]).max() < 1e-3 and np.abs(Xo - X[b]).max() < 1e-3, b
         n_cmp += 1
-    assert n_cmp >= 800                              # the oracle IPM itself fails on ~15 % of the Lanker starts
+    for b, (st_w, dw, _) in zip(failed, wres):
+        assert st_w == 1 and dw < 1e-3, (b, st_w, dw)
+    assert n_cmp + len(failed) == 1024 and n_cmp >= 800
 
 
 @pytest.mark.parametrize("name", ["ZAM_Over-1_1_LFfile", "USA_Peach-2_1_T-1", "ZAM_Tutorial-1_2_T-1", "ZAM_Tutorial_Urban-3_2"])
