@@ -8,8 +8,10 @@ dependency (casadi>=3.5.1, /root/reference/requirments:5) that is absent from th
 holds no numeric assertion for the NLP optimum.  What IS pinned (tests/test_oracle_golden.py):
 the plant model and Euler/RK4 steps against 254 recorded transitions (error 0.0), the circle geometry and the
 dynamics Jacobians against the CasADi-generated C in test/FORCESNLPsolver/FORCESNLPsolver_model.c (compiled into
-oracle/_ref by oracle/Makefile), the exact step-0 optimum a0* = -sqrt(11.5), and an independent scipy SLSQP solve.
-Statistically pinned in addition: every recorded step of the reference's own CasADi/IPOPT closed loops on ZAM_Over-1_1 (N = 10,
+oracle/_ref by oracle/Makefile), the exact step-0 optimum a0* = -sqrt(11.5), independent scipy SLSQP (N = 6) and trust-constr (N = 30 / 50, agreement 1e-6) solves,
+and the scenario inputs themselves (every recorded RMSD / deviation file of the reference reproduced to rounding,
+tests/test_results_format.py).  oracle/casadi_ref.py holds the verbatim casadi/IPOPT branch for boxes where casadi imports.
+Statistically pinned in addition: every recorded step of the reference's own CasADi/IPOPT closed loops on ZAM_Over-1_1 and USA_Lanker-2_18_T-1 (N = 10,
 applied control = optimum + N(0, sigma^2)) re-solved here leaves residuals with zero median and spread sigma
 (tests/test_oracle_golden.py::test_recorded_ipopt_controls_pin_the_oracle_optimum_statistically).
 

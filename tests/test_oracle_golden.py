@@ -207,3 +207,49 @@ def test_recorded_ipopt_controls_pin_the_oracle_optimum_statistically(key, name,
         assert abs(e[inl].mean()) < 4 * se
         mad_sigma = 1.4826 * np.median(np.abs(e - np.median(e)))
         assert 0.5 * sigma < mad_sigma < 1.5 * sigma
+
+
+def _trust_constr(d, w0):
+    """scipy's trust-region interior-point method on the restated NLP (analytic Jacobian / Hessian from oracle.nlp): an
+    implementation that shares no code with oracle/ipm.py.  The 3x duplicated obstacle rows (Q6) are passed once (LICQ)."""
+    import scipy.sparse as sp
+    from scipy.optimize import Bounds, NonlinearConstraint, minimize
+    N = d.N
+    lbg, ubg, lbx, ubx = nlp.g_bounds(d)
+    keep = np.concatenate([np.arange(1 + 5 * (N + 1)), 1 + 5 * (N + 1) + np.arange(0, 9 * (N + 1), 3)])
+    con = NonlinearConstraint(lambda w: nlp.g_fun(d, w)[keep], lbg[keep], ubg[keep], jac=lambda w: nlp.g_jac(d, w)[keep],
+                              hess=lambda w, v: nlp.lag_hess(d, w, np.bincount(keep, weights=v, minlength=d.m), 0.0))
+    return minimize(lambda w: nlp.cost(d, w), w0, jac=lambda w: nlp.cost_grad(d, w), hess=lambda w: sp.diags(nlp.cost_hess_diag(d)),
+                    method="trust-constr", constraints=[con], bounds=Bounds(lbx, ubx),
+                    options=dict(xtol=1e-12, gtol=1e-10, barrier_tol=1e-10, maxiter=3000))
+
+
+@pytest.mark.parametrize("name,N,b", [("ZAM_Over-1_1_LF", 30, 0), ("USA_Lanker-2_18_T-1_LF", 50, 1)])
+def test_oracle_vs_scipy_trust_constr_at_benchmark_horizons(name, N, b):
+    """two independent solvers on the restated NLP at the benchmark sizes (N = 30 / 50, multiple shooting, all 14N+15
+    constraint rows): oracle/ipm.py and scipy trust-constr agree to 1e-6 from the same cold start."""
+    import mpc_b200
+    sc, x0, xref, X0, U0 = mpc_b200.make_batch(name, 4, N, 20261017)
+    d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[b], sc.static_obstacle)
+    w0 = nlp.pack(U0[b], X0[b])
+    r = ipm.solve(d, w0)
+    s = _trust_constr(d, w0)
+    assert r["status"] == 1 and s.constr_violation < 1e-9
+    assert np.abs(s.x - r["w"]).max() < 1e-6 and abs(s.fun - r["obj"]) < 1e-7 * max(1.0, abs(r["obj"]))
+
+
+def test_collision_avoidance_solver_core_point_is_a_local_optimum_for_scipy_too():
+    """Collision avoidance is multi-modal from a cold start, so the independent check is local: scipy trust-constr started AT
+    the point the solver core (float64 arithmetic, tests/host_sim) converges to must stay there."""
+    import hostsim
+    import mpc_b200
+    from test_host_logic import _cfg
+    N = 30
+    sc, x0, xref, X0, U0 = mpc_b200.make_batch("ZAM_Over-1_1_CA", 4, N, 20261018)
+    X, U, st, it, _ = hostsim.solve(_cfg(sc, N, 1, max_iter=300), xref[:1], X0[:1], U0[:1])
+    assert st[0] == 1
+    d = nlp.make_nlp(N, sc.dt, sc.weights_setting, xref[0], sc.static_obstacle)
+    w = nlp.pack(U[0], X[0])
+    assert (nlp.g_fun(d, w)[1 + 5 * (N + 1):].min() - d.r_sum) < 1e-6          # the obstacle row is active at this point
+    s = _trust_constr(d, w)
+    assert s.constr_violation < 1e-9 and np.abs(s.x - w).max() < 1e-5 and s.fun >= nlp.cost(d, w) - 1e-6
