@@ -182,10 +182,33 @@ int mpcb200_solve_scenarios(mpcb200_handle* h, const double* d_xref, const int32
  *   d_p [n][10] stage parameters [path_x, path_y, v_des, psi_ref, obstacle centre / front / rear circle x, y]
  *   d_out [n][136] = c(5) | dc/dz (5x7 row-major) | h(10) | dh/dz (10x7) | f | df/dz(7) | f_terminal | df_terminal/dz(7)
  * Stage weights Q, R, dt, wheelbases and the ego circle offset come from the handle's config; `weights_terminal` [5] (host
- * pointer) are the weight_*_terminate values.  float64 arithmetic.  The SQP solver on this formulation is not built yet (it
- * needs the Riccati sweep generalised to a non-constant input matrix and a state-input cross term); this is its linearisation. */
+ * pointer) are the weight_*_terminate values.  float64 arithmetic.  `mpcb200_forces_solve` below is the solver on top of it. */
 int mpcb200_forces_stage_eval(mpcb200_handle* h, const double* weights_terminal, const double* d_z, const double* d_p,
                               double* d_out, int32_t n, void* cuda_stream);
+
+/* The reference's FORCESPRO formulation of the MPC problem (ForcesproOptimizer, optimizer.py:86-246), one NLP per ego instance,
+ * solved to convergence on the device (csrc/forces_core.cuh: general Riccati recursion, RK4 Jacobians, friction circle at
+ * every stage, nine circle pairs per stage, terminal weights).  Replaces the generated solver's entry point
+ *   FORCESNLPsolver_solve(FORCESNLPsolver_params*, FORCESNLPsolver_output*, FORCESNLPsolver_info*, ...)
+ * (test/FORCESNLPsolver/include/FORCESNLPsolver.h:108-165, bound by interface/FORCESNLPsolver_py.py:95-179 and called from
+ * optimizer.py:320) with the same data, batched:
+ *   d_xinit  [B][5]      params.xinit            initial state [xPos, yPos, delta, v, psi]                  (optimizer.py:283)
+ *   d_params [B][N][10]  params.all_parameters   stage major: path_x, path_y, v_des, psi_ref, 3 obstacle circle centres (:313-318)
+ *   d_z_init [B][N][7]   params.x0               initial guess, stage major [deltaDot, aLong, x(5)]; NULL: xinit tiled, zero inputs
+ *   d_z      [B][N][7]   output.x01 .. xN        optimal stage variables; row 0's state is xinit                  (:328-336)
+ *   d_status [B]         exitflag                1 optimal, 0 iteration limit, 3 stalled at the float32 noise floor, -6 / -7 / -8
+ *   d_iters  [B]         info.it
+ * N = cfg.N is model.N (the number of stages, optimizer.py:204); stage weights, bounds (a_max is both the symmetric
+ * acceleration bound and the friction-circle radius, optimizer.py:108-111), dt, wheelbases, r_sum and the ego circle offset
+ * come from the handle's config; `weights_terminal` [5] (HOST pointer) are the weight_*_terminate values.  The obstacle
+ * circle centres are per stage (the reference tiles one obstacle over the stages; a moving obstacle just changes the rows).
+ * Deviations that do not change the solution set: the vacuous lower bound 0 <= aLong^2 + (v psiDot)^2 is not a row; the last
+ * stage's inputs (no cost term, no dynamics) are returned as their minimum-norm optimum 0; the circle rows are worked on as
+ * distance >= r_sum instead of distance^2 >= r_sum^2.  A float32 handle with refine_f64 runs the float64 pass on the
+ * stragglers.  Unlike FORCESPRO's SQP_NLP with maxqps = 1 (one QP per call, optimizer.py:237) the NLP is solved to
+ * convergence. */
+int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, const double* d_xinit, const double* d_params,
+                         const double* d_z_init, double* d_z, int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
 /* Introspection for benches/tests. */
 int64_t mpcb200_launch_count(const mpcb200_handle* h);       /* kernels launched by this handle so far */

@@ -57,8 +57,9 @@ MPC_HD void ks_jac_mul(const KsJac<T>& j, const T X[5][7], T Y[5][7]) {
 }
 
 // One RK4 step x+ = c(z) and its Jacobian dc/dz (5x7, z = [u; x]) by the chain rule through the four stages.
+// `inc` (optional): the increment x+ - x = h/6 (k1 + 2 k2 + 2 k3 + k4) itself, free of the cancellation in (x + inc) - x.
 template <typename T>
-MPC_HD void forces_dynamics(const ForcesConsts<T>& C, const T* z, T* xn, T dc[5][7]) {
+MPC_HD void forces_dynamics(const ForcesConsts<T>& C, const T* z, T* xn, T dc[5][7], T* inc = nullptr) {
   const T h = C.dt;
   const T* u = z; const T* x = z + 2;
   T k1[5], k2[5], k3[5], k4[5], xs[5];
@@ -87,9 +88,27 @@ MPC_HD void forces_dynamics(const ForcesConsts<T>& C, const T* z, T* xn, T dc[5]
   j = ks_jac(xs, C.l_wb);
   ks_jac_mul(j, D, K); K[2][0] += T(1); K[3][1] += T(1);
   for (int r = 0; r < 5; ++r) {
-    xn[r] = x[r] + h / T(6) * (k1[r] + T(2) * k2[r] + T(2) * k3[r] + k4[r]);
+    const T dxr = h / T(6) * (k1[r] + T(2) * k2[r] + T(2) * k3[r] + k4[r]);
+    xn[r] = x[r] + dxr;
+    if (inc) inc[r] = dxr;
     for (int c = 0; c < 7; ++c) dc[r][c] = ((c == r + 2) ? T(1) : T(0)) + h / T(6) * (A[r][c] + K[r][c]);
   }
+}
+
+// the RK4 increment alone (no Jacobian): trial points of the line search
+template <typename T>
+MPC_HD void forces_rk4_increment(const ForcesConsts<T>& C, const T* z, T* inc) {
+  const T h = C.dt;
+  const T* u = z; const T* x = z + 2;
+  T k1[5], k2[5], k3[5], k4[5], xs[5];
+  ks_rhs(x, u, C.l_wb, k1);
+  for (int r = 0; r < 5; ++r) xs[r] = x[r] + T(0.5) * h * k1[r];
+  ks_rhs(xs, u, C.l_wb, k2);
+  for (int r = 0; r < 5; ++r) xs[r] = x[r] + T(0.5) * h * k2[r];
+  ks_rhs(xs, u, C.l_wb, k3);
+  for (int r = 0; r < 5; ++r) xs[r] = x[r] + h * k3[r];
+  ks_rhs(xs, u, C.l_wb, k4);
+  for (int r = 0; r < 5; ++r) inc[r] = h / T(6) * (k1[r] + T(2) * k2[r] + T(2) * k3[r] + k4[r]);
 }
 
 // h(z,p) (10) and dh/dz (10x7): friction circle, then ego circle i x obstacle circle j squared distances, i outer, j inner

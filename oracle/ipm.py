@@ -23,8 +23,8 @@ INF = np.inf
 class _Layout:
     """v = [w ; s]; c(v) = [g_E(w) - b_E ; g_I(w) - s]; bounds on v."""
 
-    def __init__(self, d):
-        lbg, ubg, lbx, ubx = nlp.g_bounds(d)
+    def __init__(self, d, model=None):
+        lbg, ubg, lbx, ubx = (model or nlp).g_bounds(d)
         self.eq = np.where(lbg == ubg)[0]
         self.iq = np.where(lbg != ubg)[0]
         self.b_eq = lbg[self.eq]
@@ -55,9 +55,12 @@ def _push_interior(v, L, U, hasL, hasU, k1=1e-2, k2=1e-2):
     return np.minimum(np.maximum(v, lo), hi)
 
 
-def solve(d, w0, tol=1e-9, max_iter=300, mu0=0.1, verbose=False):
-    """Returns dict(w, lam_g, iters, status, kkt, obj).  status 1 = converged."""
-    lay = _Layout(d)
+def solve(d, w0, tol=1e-9, max_iter=300, mu0=0.1, verbose=False, model=None):
+    """Returns dict(w, lam_g, iters, status, kkt, obj).  status 1 = converged.
+    `model`: the module that states the NLP (g_bounds, g_fun, g_jac, cost, cost_grad, lag_hess); default oracle.nlp (the
+    CasADi formulation), oracle.forces_nlp for the FORCESPRO formulation."""
+    nlp = model or globals()["nlp"]
+    lay = _Layout(d, nlp)
     n, ms, nv = lay.n, lay.ms, lay.nv
     L, U, hasL, hasU = lay.L, lay.U, lay.hasL, lay.hasU
     Lz = np.where(hasL, L, 0.0)
@@ -223,16 +226,17 @@ def solve(d, w0, tol=1e-9, max_iter=300, mu0=0.1, verbose=False):
                   f"f {nlp.cost(d, v[:n]):.6f}")
     w = v[:n]
     return dict(w=w, lam_g=lam_to_g(lam), z_lo=zL, z_hi=zU, iters=it, status=status,
-                kkt=kkt_error(d, w)[0], obj=nlp.cost(d, w), mu=mu)
+                kkt=kkt_error(d, w, model=nlp)[0], obj=nlp.cost(d, w), mu=mu)
 
 
-def kkt_error(d, w, act_tol=1e-6):
+def kkt_error(d, w, act_tol=1e-6, model=None):
     """Algorithm-independent KKT check of a candidate primal point `w` for the reference NLP.
 
     Identifies the active set at tolerance `act_tol`, solves the least-squares multiplier problem with sign
     constraints (NNLS), and returns (max(stationarity, primal infeasibility, wrong-sign), details).
     Accepts points produced by ANY solver (the oracle IPM, scipy SLSQP, the CUDA kernel)."""
     from scipy.optimize import lsq_linear
+    nlp = model or globals()["nlp"]
     lbg, ubg, lbx, ubx = nlp.g_bounds(d)
     g = nlp.g_fun(d, w)
     J = nlp.g_jac(d, w).toarray()

@@ -10,6 +10,7 @@
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/warp_core.cuh"
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/loop_core.cuh"
 #include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/forces_model.cuh"
+#include "../../motion-planning-for-autonomous-driving-with-mpc_b200/csrc/forces_core.cuh"
 
 using namespace mpcb200;
 
@@ -101,7 +102,60 @@ static void run_loop(const mpcb200_config& cfg, const LoopData& d) {
   }
 }
 
+// ---- the FORCESPRO-formulation solver core (forces_core.cuh: the device code of mpc_forces_solve_kernel)
+template <typename T>
+struct FJob {
+  const mpcb200_config* cfg;
+  FParams<T> fp;
+  T* slab;
+  const double* xinit; const double* par; const double* Zin; double* Z;
+  HostWarp* hw;
+  int status, iters, trace;
+};
+template <typename T>
+static void forces_lane_body(int lane, void* arg) {
+  FJob<T>& J = *(FJob<T>*)arg;
+  WarpCtx w(J.hw, lane);
+  ForcesSolver<T> S(J.fp, SlabRef<T>{J.slab, 0}, w);
+  S.load(J.xinit, J.par, J.Zin);
+  ProbState<T> st;
+  S.init(st);
+  for (int it = 0; it < J.cfg->max_iter && !st.done; ++it) {
+    S.iterate(st);
+    if (J.trace && lane == 0)
+      printf("it %3d mu %.2e step %.3e rho %.2e al %.3e ap %.3e ad %.3e c1 %.3e dphi %.3e status %d\n", st.iters, (double)st.mu,
+             (double)st.kkt, (double)st.rho, (double)st.d_al, (double)st.d_ap, (double)st.d_ad, (double)st.d_c1, (double)st.d_dphi, st.status);
+  }
+  S.store(J.xinit, J.par, J.Z);
+  if (lane == 0) { J.status = st.status; J.iters = st.iters; }
+}
+template <typename T>
+static void run_forces(const mpcb200_config& cfg, const double* Pt, const double* xinit, const double* par, const double* Zin, double* Z,
+                       int* status, int* iters, int B, int trace) {
+  const int N = cfg.N;
+  FLayout L(N);
+  std::vector<T> buf(L.words + 4);
+  HostWarp hw;
+  for (int b = 0; b < B; ++b) {
+    FJob<T> J;
+    J.cfg = &cfg; J.fp.P = params_from_config<T>(cfg);
+    for (int i = 0; i < 5; ++i) J.fp.Pt[i] = (T)Pt[i];
+    J.slab = buf.data(); J.xinit = xinit + 5 * (size_t)b; J.par = par + (size_t)b * 10 * N; J.Zin = Zin ? Zin + (size_t)b * 7 * N : nullptr;
+    J.Z = Z + (size_t)b * 7 * N; J.hw = &hw; J.trace = trace; J.status = 0; J.iters = 0;
+    for (auto& v : buf) v = T(NAN);
+    hw.run(&forces_lane_body<T>, &J);
+    if (status) status[b] = J.status;
+    if (iters) iters[b] = J.iters;
+  }
+}
+
 extern "C" {
+int hostsim_forces_solve(const mpcb200_config* cfg, const double* Pt, const double* xinit, const double* par, const double* Zin, double* Z,
+                         int* status, int* iters, int B, int trace) {
+  if (cfg->precision == MPCB200_F64) run_forces<double>(*cfg, Pt, xinit, par, Zin, Z, status, iters, B, trace);
+  else run_forces<float>(*cfg, Pt, xinit, par, Zin, Z, status, iters, B, trace);
+  return 0;
+}
 int hostsim_solve_dual(const mpcb200_config* cfg, const double* xref, double* X, double* U, double* lam, int* status, int* iters, int B) {
   if (cfg->precision == MPCB200_F64) run<double>(*cfg, xref, X, U, status, iters, nullptr, B, 0, lam);
   else run<float>(*cfg, xref, X, U, status, iters, nullptr, B, 0, lam);

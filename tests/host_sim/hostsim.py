@@ -33,7 +33,7 @@ def lib():
         so = os.path.join(HERE, "libhostsim.so")
         src = os.path.join(HERE, "host_sim.cpp")
         csrc = os.path.join(HERE, "..", "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "loop_core.cuh", "forces_model.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("warp_core.cuh", "loop_core.cuh", "forces_model.cuh", "forces_core.cuh", "warp_ctx.cuh", "mpc_types.cuh", "config_params.h")]
         if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMPC_DIAG", "-shared", "-fPIC", "-o", so, src], cwd=HERE)
         _lib = C.CDLL(so)
@@ -106,3 +106,19 @@ def solve_dual(cfg, xref, X, U, lam=None):
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     lib().hostsim_solve_dual(C.byref(cfg), p(xref), p(X), p(U), p(lam), p(st), p(it), B)
     return X, U, st, it, lam
+
+
+def forces_solve(cfg, weights_terminal, xinit, params, Zin=None, trace=0):
+    """The FORCESPRO-formulation solver core (csrc/forces_core.cuh) on the emulator: xinit [B,5], params [B,N,10], optional warm
+    start Zin [B,N,7] -> (Z [B,N,7], status, iters)."""
+    xinit = np.ascontiguousarray(np.atleast_2d(xinit), np.float64)
+    B, N = xinit.shape[0], cfg.N
+    params = np.ascontiguousarray(params, np.float64).reshape(B, N, 10)
+    Pt = np.ascontiguousarray(weights_terminal, np.float64)
+    Z = np.zeros((B, N, 7))
+    st = np.zeros(B, np.int32)
+    it = np.zeros(B, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    zin = None if Zin is None else np.ascontiguousarray(Zin, np.float64)
+    lib().hostsim_forces_solve(C.byref(cfg), p(Pt), p(xinit), p(params), None if zin is None else p(zin), p(Z), p(st), p(it), B, trace)
+    return Z, st, it
