@@ -57,7 +57,8 @@ enum : int {
   FR_DX = 133,   // 5  step dx_k
   FR_DU = 138,   // 2  step du_k
   FR_FAR = 140,  // 1  circle rows of x_k screened out this iteration
-  FREC = 141     // odd: lane = stage accesses are bank-conflict free
+  FR_LC = 141,   // 5  multiplier-weighted gradient of the x_k terms (adjoint recursion of the dynamics-curvature term)
+  FREC = 147     // odd: lane = stage accesses are bank-conflict free
 };
 // state record k = 0..N-1
 enum : int {
@@ -66,7 +67,8 @@ enum : int {
   FS_XTT = 10,   // 5 trial deviation state
   FS_OB = 15,    // 6 obstacle circle centres of this stage (relative to xinit)
   FS_CP = 21,    // 2 reference position increment ref_k - ref_{k+1}, formed in float64
-  FST = 23
+  FS_TR = 23,    // 3 sin(psi_k) cos(psi_k) tan(delta_k) at the current iterate
+  FST = 27
 };
 enum : int { FH00 = 0, FH01, FH04, FH11, FH14, FH44, FH22, FH23, FH33 };
 
@@ -90,6 +92,7 @@ struct FLaneTab {
   int so0, so1;     // S[c][j] (gradient r_c on the affine column)
   int si1;          // S[1][i]
   int aij, bi0, bi1;
+  int exw;          // dynamics-curvature addition: 0 none, 1 (4,4), 2 (3,4), 3 (2,2), 4 (2,3)
   MPC_HD explicit FLaneTab(int lane) {
     const int l = lane < 30 ? lane : 0;
     i = l / 6; j = l % 6;
@@ -118,6 +121,8 @@ struct FLaneTab {
     si1 = (i == 2) ? FR_SX : (i == 3) ? (FR_SX + 1) : FR_ZERO;
     aij = (j == 5) ? (FR_D + i) : (FR_A + 5 * i + j);
     bi0 = FR_B + 2 * i; bi1 = FR_B + 2 * i + 1;
+    exw = 0;
+    if (j < 5 && i <= j) { if (i == 4 && j == 4) exw = 1; if (i == 3 && j == 4) exw = 2; if (i == 2 && j == 2) exw = 3; if (i == 2 && j == 3) exw = 4; }
   }
 };
 
@@ -318,26 +323,29 @@ struct ForcesSolver {
         for (int q = 0; q < 5; ++q) rc(k, FR_D + q) = T(0);
       }
       // x_k terms (k >= 1; x_0 is fixed)
-      T hd[5] = {T(0), T(0), T(0), T(0), T(0)}, g[5] = {T(0), T(0), T(0), T(0), T(0)};
+      T hd[5] = {T(0), T(0), T(0), T(0), T(0)}, g[5] = {T(0), T(0), T(0), T(0), T(0)}, lc[5] = {T(0), T(0), T(0), T(0), T(0)};
       T h01 = T(0), h04 = T(0), h14 = T(0), h23 = T(0);
       bool far = true;
+      T sn, cs; m_sincos(xa[4], &sn, &cs);
+      sx(k, FS_TR) = sn; sx(k, FS_TR + 1) = cs; sx(k, FS_TR + 2) = m_tan(xa[2]);
       if (k >= 1) {
         const T* wq = term ? Pt : P.Q;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) { hd[q] = T(2) * wq[q]; g[q] = T(2) * wq[q] * xd[q]; }
+        for (int q = 0; q < 5; ++q) { hd[q] = T(2) * wq[q]; g[q] = T(2) * wq[q] * xd[q]; lc[q] = g[q]; }
         {
           const T ilo = m_rcp(m_slack(xa[2] - P.de_min)), ihi = m_rcp(m_slack(P.de_max - xa[2]));
           hd[2] += rc(k, FR_V + FV_DE_LO) * ilo + rc(k, FR_V + FV_DE_HI) * ihi;
           g[2] += mu * (ihi - ilo);
+          lc[2] += rc(k, FR_V + FV_DE_HI) - rc(k, FR_V + FV_DE_LO);
         }
         {
           const T ilo = m_rcp(m_slack(xa[3] - P.v_min)), ihi = m_rcp(m_slack(P.v_max - xa[3]));
           hd[3] += rc(k, FR_V + FV_V_LO) * ilo + rc(k, FR_V + FV_V_HI) * ihi;
           g[3] += mu * (ihi - ilo);
+          lc[3] += rc(k, FR_V + FV_V_HI) - rc(k, FR_V + FV_V_LO);
         }
         far = is_far(k, xa[0], xa[1], mu);
         if (!far) {
-          T sn, cs; m_sincos(xa[4], &sn, &cs);
 #pragma unroll
           for (int e = 0; e < 3; ++e) {
 #pragma unroll
@@ -352,6 +360,7 @@ struct ForcesSolver {
               hd[0] += wgt * gx * gx; h01 += wgt * gx * gy; h04 += wgt * gx * gp;
               hd[1] += wgt * gy * gy; h14 += wgt * gy * gp; hd[4] += wgt * gp * gp;
               g[0] += cg * gx; g[1] += cg * gy; g[4] += cg * gp;
+              lc[0] -= nu * gx; lc[1] -= nu * gy; lc[4] -= nu * gp;
             }
           }
         }
@@ -385,9 +394,12 @@ struct ForcesSolver {
           h23 += wgt * f.gde * f.gv + T(2) * nu * f.qd * f.qv;
           hd[3] += wgt * f.gv * f.gv + T(2) * nu * f.qv * f.qv;
           g[2] += cg * f.gde; g[3] += cg * f.gv;
+          lc[2] -= nu * f.gde; lc[3] -= nu * f.gv;
           sx0 = wgt * f.ga * f.gde; sx1 = wgt * f.ga * f.gv;
         }
       }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) rc(k, FR_LC + q) = lc[q];
       rc(k, FR_H + FH00) = hd[0]; rc(k, FR_H + FH01) = h01; rc(k, FR_H + FH04) = h04; rc(k, FR_H + FH11) = hd[1];
       rc(k, FR_H + FH14) = h14; rc(k, FR_H + FH44) = hd[4]; rc(k, FR_H + FH22) = hd[2]; rc(k, FR_H + FH23) = h23; rc(k, FR_H + FH33) = hd[3];
 #pragma unroll
@@ -399,9 +411,17 @@ struct ForcesSolver {
   }
 
   // ------------------------------------------------------------------ phase C: backward Riccati sweep (lane = entry of [P | p])
-  MPC_HD void backward() const {
+  // EX: the curvature of the dynamics rows, sum_i lam_{k+1,i} hess c_i(z_k), is added to the state block with the adjoint
+  // multipliers lam_k = lc_k + A_k' lam_{k+1} (every lane keeps the 5-vector) and the CONTINUOUS-TIME second derivatives times dt
+  // (the RK4 step's own second derivative differs by O(dt^2); a Hessian approximation only has to be good enough for the
+  // iteration to contract -- measured: with position weights of 200 against a heading weight of 1 (USA_Lanker) the pure
+  // Gauss-Newton iteration DIVERGES at rate 1.1 near the solution).  Returns false (uniformly) if an input block is not positive
+  // definite; the caller then repeats the sweep without the term.
+  template <bool EX>
+  MPC_HD bool backward_t() const {
     const int N = P.N;
     T Pij = T(0);
+    T lam[5] = {T(0), T(0), T(0), T(0), T(0)};
     const T ownf = (T)tb.own;
     for (int k = N - 1; k >= 0; --k) {
       const int o = L.o_rec + FREC * k;
@@ -428,15 +448,45 @@ struct ForcesSolver {
         Fxx += sl[o + tb.ai[l]] * mlj;
       }
       const T det = G00 * G11 - G01 * G01;
+      if (EX) {
+        if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) return false;      // uniform across lanes
+      }
       const T cdet = m_rcp(det);
       const T J00 = -cdet * G11, J01 = cdet * G01, J11 = -cdet * G00;
       const T T0 = J00 * F0j + J01 * F1j, T1 = J01 * F0j + J11 * F1j;      // gains [K | kff] column j
+      if (EX) {
+        const T dt = P.dt, il = T(1) / P.l_wb;
+        const T v = sx(k, FS_XT + 3) + sx(k, FS_XR + 3);
+        const T sn = sx(k, FS_TR), cs = sx(k, FS_TR + 1), tn = sx(k, FS_TR + 2);
+        const T sec2 = T(1) + tn * tn;
+        T ex = T(0);
+        if (tb.exw == 1) ex = -dt * v * (lam[0] * cs + lam[1] * sn);
+        if (tb.exw == 2) ex = dt * (lam[1] * cs - lam[0] * sn);
+        if (tb.exw == 3) ex = dt * lam[4] * T(2) * v * il * sec2 * tn;
+        if (tb.exw == 4) ex = dt * lam[4] * sec2 * il;
+        Fxx += ex;
+        T ln[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          T acc = sl[o + FR_LC + c];
+#pragma unroll
+          for (int l = 0; l < 5; ++l) acc += sl[o + FR_A + 5 * l + c] * lam[l];
+          ln[c] = acc;
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) lam[c] = ln[c];
+      }
       const T Pn = Fxx + F0i * T0 + F1i * T1;
       if (lane < 6) { sl[o + FR_KK + tb.j] = T0; sl[o + FR_KK + 6 + tb.j] = T1; }
       if (lane < 30) sl[o + FR_ACL + lane] = sl[o + tb.aij] + sl[o + tb.bi0] * T0 + sl[o + tb.bi1] * T1;
       Pij = Pn;
     }
     w.sync();
+    return true;
+  }
+  MPC_HD void backward() const {
+    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; w.sync(); }
+    backward_t<false>();
   }
 
   // ------------------------------------------------------------------ phase D: forward sweep
@@ -457,11 +507,15 @@ struct ForcesSolver {
   }
 
   // ------------------------------------------------------------------ phase E: step-length limits, merit slope (lane = stage)
-  struct FwdOut { T a_p, a_d, dphi, c1, step_inf, mag; };
+  struct FwdOut { T a_p, a_d, dphi, c1, step_inf, mag; int blk, cur; };
   MPC_HD void row_limits(T s, T nu, T ds, T mu, FwdOut& o) const {
     const T is = m_rcp(s), inu = m_rcp(nu);
     const T t = ds * is;
     const T q = (mu * is) * inu - T(1) - t;
+#ifdef MPC_DIAG
+    if (-t > o.a_p) o.blk = o.cur;
+    o.cur++;
+#endif
     o.a_p = m_max(o.a_p, -t);
     o.a_d = m_max(o.a_d, -q);
     o.dphi -= mu * t;
@@ -470,8 +524,9 @@ struct ForcesSolver {
     const int N = P.N;
     const T mu = st.mu;
     const T tau = m_max(P.tau_min, T(1) - mu);
-    FwdOut o; o.a_p = T(0); o.a_d = T(0); o.dphi = T(0); o.c1 = T(0); o.step_inf = T(0); o.mag = T(0);
+    FwdOut o; o.a_p = T(0); o.a_d = T(0); o.dphi = T(0); o.c1 = T(0); o.step_inf = T(0); o.mag = T(0); o.blk = -1; o.cur = 0;
     for (int k = lane; k < N; k += 32) {
+      o.cur = 32 * k;
       T xd[5], xa[5], dx[5];
 #pragma unroll
       for (int q = 0; q < 5; ++q) { xd[q] = sx(k, FS_XT + q); xa[q] = xd[q] + sx(k, FS_XR + q); dx[q] = rc(k, FR_DX + q); }
@@ -523,6 +578,11 @@ struct ForcesSolver {
     }
     const bool fin = m_finite(o.step_inf) && m_finite(o.dphi) && m_finite(o.a_p) && m_finite(o.a_d);
     const bool allfin = w.all(fin);
+#ifdef MPC_DIAG
+    { const T mine = o.a_p; const T mx = w.max_nonneg(m_max(o.a_p, T(0))); int code = (mine == mx) ? o.blk : -1;
+      for (int m = 16; m; m >>= 1) { const int other = w.shfl_xor(code, m); code = code > other ? code : other; }
+      o.blk = code; }
+#endif
     o.a_p = w.max_nonneg(m_max(o.a_p, T(0))); o.a_d = w.max_nonneg(m_max(o.a_d, T(0)));
     o.a_p = (o.a_p > tau) ? tau * m_rcp(o.a_p) : T(1);
     o.a_d = (o.a_d > tau) ? tau * m_rcp(o.a_d) : T(1);
@@ -737,10 +797,12 @@ struct ForcesSolver {
     const bool trust = (f.c1 <= cfloor) && (f.step_inf <= P.trust_step);
     T al = f.a_p;
     bool accepted = false;
+    T c1_new = f.c1;                                       // l1 infeasibility at the point the step leads to
     for (int t = 0; t < P.ls_max; ++t) {
       T dphi, c1, nz;
       trial_points(al);
       const bool ok = trial_merit(st, al, dphi, c1, nz);
+      if (ok && m_finite(c1)) c1_new = c1;
       const T dm = dphi + st.rho * (c1 - f.c1);
       const T noise = T(8) * epsm * (nz + st.rho * f.mag);
       if (ok && m_finite(dm) && dm <= T(1e-4) * al * slope + noise) { accepted = true; break; }
@@ -756,7 +818,7 @@ struct ForcesSolver {
     }
     T avg, cmax, smin_nl;
     commit(st, al, f.a_d, avg, cmax, smin_nl);
-    st.d_al = al; st.d_ap = f.a_p; st.d_ad = f.a_d; st.d_c1 = f.c1; st.d_dphi = f.dphi;
+    st.d_al = al; st.d_ap = f.a_p; st.d_ad = f.a_d; st.d_c1 = f.c1; st.d_dphi = f.dphi; st.d_blk = f.blk;
     st.iters++;
     st.kkt = f.step_inf;
     if (st.mu <= P.mu_min * T(1.0001) && f.c1 <= P.tol_feas) {
@@ -783,10 +845,23 @@ struct ForcesSolver {
     }
     if (al >= P.mu_min_alpha) {
       const T fac = (al >= T(1) && f.a_d >= T(1)) ? P.mu_factor_full : P.mu_factor;
-      const T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(fac * avg, avg * m_sqrt_fast(avg))));
+      T mu_new = m_max(P.mu_min, m_min(st.mu, m_min(fac * avg, avg * m_sqrt_fast(avg))));
+      // the barrier parameter does not run ahead of feasibility (IPOPT lowers mu only once the barrier problem's error --
+      // which includes the primal infeasibility -- is below kappa_eps mu): with mu ~ 1e-7 and defects still O(1) the next
+      // steps are cut to 1e-3 by the fraction-to-the-boundary rule and the iteration jams on the bounds (measured: the tail
+      // of the perturbed batches, 15 - 70 iterations instead of 6)
+      mu_new = m_max(mu_new, m_min(st.mu, mu_feas() * c1_new));
       if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
       st.mu = mu_new;
     }
+  }
+  MPC_HD static T mu_feas() {
+#if !defined(__CUDACC__) && defined(MPC_DIAG)
+    static const T v = getenv("FORCES_MU_FEAS") ? (T)atof(getenv("FORCES_MU_FEAS")) : T(1e-3);
+    return v;
+#else
+    return T(1e-3);
+#endif
   }
 };
 

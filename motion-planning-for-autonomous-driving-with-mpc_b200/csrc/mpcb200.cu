@@ -15,62 +15,12 @@
 //   * batch 1024 = 512 CTAs x 2 warps over 148 SMs (6-8 warps per SM, every SM busy); larger batches run in waves
 //     scheduled by the hardware (up to 8 CTAs of 27.7 KB resident per SM in the Gauss-Newton kernels).
 // Tensor cores are not used: the factorisation works on 5x5/2x2 stage blocks along a length-N dependency chain.
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-#include <stdlib.h>
-#include <string>
-#include <new>
-
-#include "config_params.h"
-#include "warp_core.cuh"
+#include "mpcb200_internal.cuh"
 #include "loop_core.cuh"
 #include "forces_model.cuh"
-#include "forces_core.cuh"
-
-using namespace mpcb200;
-
-// ===================================================================================================== PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// TMA 1-D bulk copy shared -> global (bulk-group completion)
-__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
 
 // ===================================================================================================== kernel args
 enum : int { MODE_ONESHOT = 0, MODE_BEGIN = 1, MODE_ITER = 2, MODE_END = 3 };
-
-// device-side work counters of a handle (self-resetting: the last warp to leave a launch that used them zeroes them)
-struct WorkCtr {
-  int next;       // next unclaimed work item beyond the statically assigned first wave
-  int done;       // warps that have left the launch
-  int q_count;    // refinement queue: problems the float32 pass did not bring to status 1
-  int q_pad;
-};
 
 template <typename T>
 struct SolveArgs {
@@ -381,90 +331,6 @@ __global__ void __launch_bounds__(32 * WPC) mpc_warp_closed_loop_kernel(const __
   }
 }
 
-// ===================================================================================================== FORCESPRO formulation
-// One warp per ego instance on the reference's FORCESPRO formulation of the MPC problem (forces_core.cuh), persistent warps with
-// dynamic work claiming like the CasADi-formulation kernel.  The problem's parameter block ([N][10] float64 = 80 N bytes, always a
-// multiple of 16) comes HBM -> shared memory by ONE TMA bulk copy per problem when its address is 16-byte aligned (plain loads
-// otherwise); the KKT slab (164 N words) lives in shared memory for the whole solve; Z goes back lane = stage.
-template <typename T>
-struct ForcesArgs {
-  FParams<T> fp;
-  const double* xinit;   // [B][5]
-  const double* par;     // [B][N][10]
-  const double* Zin;     // [B][N][7] warm start or null
-  double* Z;             // [B][N][7]
-  int* status; int* iters;
-  WorkCtr* ctr; int* q_list;
-  int B, refine, dynamic, pdl_primary;
-};
-static size_t forces_smem_bytes_for(int N, int words, size_t elem, int wpc) {
-  return (size_t)wpc * ((size_t)words * elem + (size_t)10 * N * sizeof(double));
-}
-
-template <typename T, int WPC>
-__global__ void __launch_bounds__(32 * WPC) mpc_forces_solve_kernel(const __grid_constant__ ForcesArgs<T> a) {
-  unsigned char* const smem_raw = mpc_dyn_smem;
-  __shared__ __align__(8) uint64_t bar_p[WPC];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.fp.P.N;
-  const FLayout L(N);
-  const int total_warps = gridDim.x * WPC;
-  double* const stg = reinterpret_cast<double*>(smem_raw + (size_t)WPC * L.words * sizeof(T)) + (size_t)wid * 10 * N;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < WPC; ++i) mbar_init(&bar_p[i], 1);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  if (a.pdl_primary) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (a.refine) asm volatile("griddepcontrol.wait;" ::: "memory");
-  const WarpCtx w;
-  ForcesSolver<T> S(a.fp, SlabRef<T>{wid * L.words}, w);
-  const int nwork = a.refine ? a.ctr->q_count : a.B;
-  uint32_t ph = 0;
-  for (int item = blockIdx.x * WPC + wid; item < nwork;) {
-    const int b = a.refine ? a.q_list[item] : item;
-    const double* gpar = a.par + (size_t)b * 10 * N;
-    const double* par = gpar;
-    if ((((uintptr_t)gpar) & 15u) == 0) {
-      fence_async_smem();                        // the staging was last read through the generic proxy (previous problem)
-      __syncwarp();
-      if (lane == 0) {
-        mbar_expect_tx(&bar_p[wid], (uint32_t)(80 * N));
-        tma_load_1d(stg, gpar, (uint32_t)(80 * N), &bar_p[wid]);
-      }
-      mbar_wait(&bar_p[wid], ph);
-      ph ^= 1u;
-      __syncwarp();
-      par = stg;
-    }
-    const double* xin = a.xinit + (size_t)b * 5;
-    // refinement pass: warm start = the float32 result
-    const double* zin = a.refine ? (a.Z + (size_t)b * 7 * N) : (a.Zin ? a.Zin + (size_t)b * 7 * N : nullptr);
-    ProbState<T> st;
-    S.load(xin, par, zin);
-    S.init(st);
-    for (int it = 0; it < a.fp.P.max_iter && !st.done; ++it) S.iterate(st);
-    S.store(xin, par, a.Z + (size_t)b * 7 * N);
-    if (lane == 0) {
-      if (a.status) a.status[b] = st.status;
-      if (a.iters) a.iters[b] = st.iters + (a.refine ? a.iters[b] : 0);
-      if (a.q_list && !a.refine && st.status != ST_OPTIMAL && st.status != ST_INFEASIBLE_X0) a.q_list[atomicAdd(&a.ctr->q_count, 1)] = b;
-    }
-    if (!a.dynamic) break;
-    int nxt = 0;
-    if (lane == 0) nxt = total_warps + atomicAdd(&a.ctr->next, 1);
-    item = __shfl_sync(0xffffffffu, nxt, 0);
-  }
-  if ((a.dynamic || a.refine) && lane == 0 && !(a.refine && nwork == 0)) {
-    __threadfence();
-    if (atomicAdd(&a.ctr->done, 1) == total_warps - 1) {
-      a.ctr->next = 0; a.ctr->done = 0;
-      if (a.refine) a.ctr->q_count = 0;
-    }
-  }
-}
-
 // ===================================================================================================== small kernels
 __global__ void plant_step_shift_kernel(double* x, double* U, double* X, double* u_applied, int B, int N, double dt, double l_wb) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,64 +375,6 @@ __global__ void __launch_bounds__(32) forces_stage_eval_kernel(ForcesConsts<doub
     const int r = e / FORCES_OUT_WORDS, c = e - r * FORCES_OUT_WORDS;
     out[(size_t)base * FORCES_OUT_WORDS + e] = stage[r * (FORCES_OUT_WORDS + 1) + c];
   }
-}
-
-// ===================================================================================================== handle
-#define MPCB200_HOST_STREAMS 4
-struct KernelPlan {     // launch shape of one kernel family (solve / refinement / closed loop) for this handle
-  int wpc;              // warps (= problems) per CTA
-  size_t smem;          // dynamic shared memory per CTA
-  int max_ctas;         // resident CTAs on the device (SM count x occupancy): the persistent grid never exceeds it
-};
-struct mpcb200_handle {
-  mpcb200_config cfg;
-  KernelPlan solve, refine, loop;
-  int words;            // slab words per problem
-  void* slab;           // global slab image [max_batch][words] (stepwise mode), allocated on first use
-  void* state;
-  void* obs_shift;
-  WorkCtr* ctr;         // device work counters (zeroed at create, self-resetting afterwards)
-  int* q_list;          // [max_batch] refinement queue (refine_f64 handles)
-  mpcb200_scenario* scn_table;   // device copy of the scenario table (mpcb200_set_scenarios)
-  int n_scn;
-  KernelPlan scn, scn_refine;    // launch shapes of the per-problem-scenario kernels (planned at set_scenarios)
-  KernelPlan forces, forces_refine;   // FORCESPRO-formulation kernels (planned at the first mpcb200_forces_solve)
-  int forces_planned;
-  size_t elem;          // sizeof(T)
-  int64_t launches;
-  // stepwise-mode context
-  const double* sw_xref;
-  int sw_B;
-  // host-path staging
-  double *d_xref, *d_X, *d_U;
-  int *d_status, *d_iters;
-  cudaStream_t hs[MPCB200_HOST_STREAMS];
-  int* h_pin;           // pinned host staging for status + iters (a pageable D2H target would serialise the chunk pipeline)
-  std::string err;
-};
-
-static thread_local std::string g_create_err;
-
-static int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
-  char buf[512];
-  snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
-  if (h) h->err = buf; else g_create_err = buf;
-  return -1;
-}
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
-
-// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
-struct DeviceGuard {
-  int prev; bool switched;
-  explicit DeviceGuard(int dev) : prev(-1), switched(false) {
-    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
-  }
-  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
-};
-
-static int grid_for(const KernelPlan& k, int nwork) {
-  const int want = (nwork + k.wpc - 1) / k.wpc;
-  return want < k.max_ctas ? want : k.max_ctas;
 }
 
 template <typename T, int WPC, int HM>
@@ -619,23 +427,6 @@ static cudaError_t dispatch_loop(mpcb200_handle* h, LoopArgs<T>& a, cudaStream_t
   return e;
 }
 
-// Opt every instantiation this handle can launch in to the device's FULL opt-in shared memory (a property of the function on
-// the device, shared by all handles: never a per-handle size, so one handle cannot lower another's limit), and ask the
-// occupancy calculator how many CTAs of the handle's size stay resident.
-template <typename K>
-static cudaError_t plan_kernel(K kern, int wpc, size_t smem, int optin, int sms, int* max_ctas) {
-  cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * wpc, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) return cudaErrorInvalidConfiguration;
-  *max_ctas = occ * sms;
-  return cudaSuccess;
-}
 template <typename T>
 static cudaError_t plan_solve(KernelPlan& k, bool exact, int optin, int sms) {
   cudaError_t e = cudaSuccess;
@@ -773,88 +564,29 @@ static void fill_scn_args(mpcb200_handle* h, ScnArgs<T>& a, const double* xref, 
   a.ctr = h->ctr; a.q_list = nullptr; a.B = B; a.refine = 0; a.dynamic = 0; a.pdl_primary = 0;
 }
 
-template <typename T>
-static cudaError_t plan_forces(KernelPlan& k, int optin, int sms) {
-  switch (k.wpc) {
-    case 2: return plan_kernel(mpc_forces_solve_kernel<T, 2>, 2, k.smem, optin, sms, &k.max_ctas);
-    default: k.wpc = 1; return plan_kernel(mpc_forces_solve_kernel<T, 1>, 1, k.smem, optin, sms, &k.max_ctas);
-  }
-}
-template <typename T>
-static cudaError_t launch_forces(mpcb200_handle* h, ForcesArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
-  const int ctas = grid_for(k, nwork);
-  a.dynamic = (a.refine || nwork > ctas * k.wpc) ? 1 : 0;
-  h->launches++;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(32 * k.wpc); cfg.dynamicSmemBytes = k.smem; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = a.refine ? 1 : 0;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  if (k.wpc == 2) return cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 2>, a);
-  return cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 1>, a);
-}
-template <typename T>
-static void fill_forces_args(mpcb200_handle* h, ForcesArgs<T>& a, const double* wt, const double* xinit, const double* par, const double* Zin,
-                             double* Z, int32_t* status, int32_t* iters, int32_t B) {
-  a.fp.P = params_from_config<T>(h->cfg);
-  for (int i = 0; i < 5; ++i) a.fp.Pt[i] = (T)wt[i];
-  a.xinit = xinit; a.par = par; a.Zin = Zin; a.Z = Z; a.status = status; a.iters = iters;
-  a.ctr = h->ctr; a.q_list = nullptr; a.B = B; a.refine = 0; a.dynamic = 0; a.pdl_primary = 0;
-}
-static int ensure_forces_plan(mpcb200_handle* h) {
-  if (h->forces_planned) return 0;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, h->cfg.device));
-  const int optin = (int)prop.sharedMemPerBlockOptin, sms = prop.multiProcessorCount;
-  const size_t smem_max = prop.sharedMemPerBlockOptin;
-  const bool f64 = h->cfg.precision == MPCB200_F64;
-  const FLayout L(h->cfg.N);
-  const int pref = (h->cfg.warps_per_cta == 1) ? 1 : 2;
-  const int cand[2] = {pref, 1};
-  bool fits = false;
-  for (int i = 0; i < 2 && !fits; ++i) {
-    const size_t need = forces_smem_bytes_for(h->cfg.N, L.words, h->elem, cand[i]);
-    if (need + 1024 <= smem_max) { h->forces.wpc = cand[i]; h->forces.smem = need; fits = true; }
-  }
-  if (!fits) { h->err = "horizon too long: the FORCESPRO-formulation KKT slab does not fit shared memory"; return -2; }
-  cudaError_t e = f64 ? plan_forces<double>(h->forces, optin, sms) : plan_forces<float>(h->forces, optin, sms);
-  if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO formulation)", e);
-  h->forces_refine.wpc = 0;
-  if (!f64 && h->cfg.refine_f64 && h->q_list) {
-    h->forces_refine.wpc = 1; h->forces_refine.smem = forces_smem_bytes_for(h->cfg.N, L.words, 8, 1);
-    if (h->forces_refine.smem + 1024 > smem_max) { h->err = "horizon too long for the float64 refinement pass (FORCESPRO formulation)"; return -2; }
-    e = plan_forces<double>(h->forces_refine, optin, sms);
-    if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO formulation, float64 refinement)", e);
-    if (h->forces_refine.max_ctas > sms) h->forces_refine.max_ctas = sms;
-  }
-  h->forces_planned = 1;
-  return 0;
-}
-
 extern "C" {
 
 int32_t mpcb200_abi_version(void) { return MPCB200_ABI_VERSION; }
 
 void mpcb200_default_config(mpcb200_config* cfg, int32_t N, int32_t precision) { default_config(cfg, N, precision); }
 
-const char* mpcb200_last_error(const mpcb200_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+const char* mpcb200_last_error(const mpcb200_handle* h) { return h ? h->err.c_str() : create_err().c_str(); }
 
 int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   mpcb200_handle* h = nullptr;
-  if (!cfg || !out) { g_create_err = "null argument"; return -2; }
-  if (cfg->abi_version != MPCB200_ABI_VERSION) { g_create_err = "abi_version mismatch"; return -2; }
-  if (cfg->N < 4 || cfg->N > 128 || cfg->max_batch < 1) { g_create_err = "N must be in [4, 128] (tested range), max_batch >= 1"; return -2; }
+  if (!cfg || !out) { create_err() = "null argument"; return -2; }
+  if (cfg->abi_version != MPCB200_ABI_VERSION) { create_err() = "abi_version mismatch"; return -2; }
+  if (cfg->N < 4 || cfg->N > 128 || cfg->max_batch < 1) { create_err() = "N must be in [4, 128] (tested range), max_batch >= 1"; return -2; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) { fail(nullptr, "no CUDA device (libmpcb200 has no CPU path)", e); return -3; }
-  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "cfg.device out of range"; return -2; }
+  if (cfg->device < 0 || cfg->device >= ndev) { create_err() = "cfg.device out of range"; return -2; }
   DeviceGuard guard(cfg->device);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
-  if (prop.major < 9) { g_create_err = "libmpcb200 needs TMA bulk copies (sm_90+); built for sm_100a"; return -3; }
+  if (prop.major < 9) { create_err() = "libmpcb200 needs TMA bulk copies (sm_90+); built for sm_100a"; return -3; }
   h = new (std::nothrow) mpcb200_handle();
-  if (!h) { g_create_err = "out of host memory"; return -4; }
+  if (!h) { create_err() = "out of host memory"; return -4; }
   h->cfg = *cfg;
   h->launches = 0; h->slab = h->state = h->obs_shift = nullptr; h->ctr = nullptr; h->q_list = nullptr; h->scn_table = nullptr; h->n_scn = 0; h->forces_planned = 0;
   h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
@@ -869,7 +601,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   const int pref = (cfg->warps_per_cta == 1 || cfg->warps_per_cta == 2 || cfg->warps_per_cta == 4) ? cfg->warps_per_cta : 2;
   if (!choose_wpc(h->solve, pref, smem_bytes_for, cfg->N, L.words, h->elem, smem_max) ||
       !choose_wpc(h->loop, pref, loop_smem_bytes_for, cfg->N, L.words, h->elem, smem_max)) {
-    g_create_err = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2;
+    create_err() = "horizon too long: the per-problem KKT slab does not fit shared memory"; delete h; return -2;
   }
   e = f64 ? plan_solve<double>(h->solve, exact, optin, sms) : plan_solve<float>(h->solve, exact, optin, sms);
   if (e == cudaSuccess) e = f64 ? plan_loop<double>(h->loop, exact, optin, sms) : plan_loop<float>(h->loop, exact, optin, sms);
@@ -877,7 +609,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   h->refine.wpc = 0;
   if (!f64 && cfg->refine_f64) {
     if (!choose_wpc(h->refine, 1, smem_bytes_for, cfg->N, L.words, 8, smem_max)) {
-      g_create_err = "horizon too long for the float64 refinement pass"; delete h; return -2;
+      create_err() = "horizon too long for the float64 refinement pass"; delete h; return -2;
     }
     e = plan_solve<double>(h->refine, exact, optin, sms);
     if (e != cudaSuccess) { fail(nullptr, "kernel configuration (float64 refinement)", e); delete h; return -1; }
@@ -1141,36 +873,6 @@ int mpcb200_forces_stage_eval(mpcb200_handle* h, const double* weights_terminal,
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, "forces_stage_eval launch", e);
-  return 0;
-}
-
-int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, const double* d_xinit, const double* d_params, const double* d_z_init,
-                         double* d_z, int32_t* d_status, int32_t* d_iters, int32_t B, void* stream) {
-  if (!h) return -2;
-  if (B <= 0) return 0;
-  if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
-  if (!weights_terminal || !d_xinit || !d_params || !d_z) { h->err = "null argument"; return -2; }
-  if (((uintptr_t)d_xinit | (uintptr_t)d_params | (uintptr_t)d_z_init | (uintptr_t)d_z) & 7u) { h->err = "float64 arrays must be 8-byte aligned"; return -2; }
-  DeviceGuard guard(h->cfg.device);
-  int rc = ensure_forces_plan(h);
-  if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e;
-  if (h->cfg.precision == MPCB200_F64) {
-    ForcesArgs<double> a; fill_forces_args(h, a, weights_terminal, d_xinit, d_params, d_z_init, d_z, d_status, d_iters, B);
-    e = launch_forces<double>(h, a, s, h->forces, B);
-  } else {
-    const bool refine = h->cfg.refine_f64 && d_status && h->forces_refine.wpc;
-    ForcesArgs<float> a; fill_forces_args(h, a, weights_terminal, d_xinit, d_params, d_z_init, d_z, d_status, d_iters, B);
-    a.q_list = refine ? h->q_list : nullptr; a.pdl_primary = refine ? 1 : 0;
-    e = launch_forces<float>(h, a, s, h->forces, B);
-    if (e == cudaSuccess && refine) {
-      ForcesArgs<double> r; fill_forces_args(h, r, weights_terminal, d_xinit, d_params, d_z_init, d_z, d_status, d_iters, B);
-      r.q_list = h->q_list; r.refine = 1;
-      e = launch_forces<double>(h, r, s, h->forces_refine, B);
-    }
-  }
-  if (e != cudaSuccess) return fail(h, "mpc_forces_solve_kernel launch", e);
   return 0;
 }
 

@@ -1,0 +1,129 @@
+// mpcb200_internal.cuh -- what the translation units of libmpcb200.so share: PTX helpers (mbarrier, TMA bulk copies), the handle,
+// launch planning.  Not part of the C ABI (include/mpcb200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <new>
+
+#include "config_params.h"
+#include "warp_core.cuh"
+
+using namespace mpcb200;
+
+// ===================================================================================================== PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk-group completion)
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// device-side work counters of a handle (self-resetting: the last warp to leave a launch that used them zeroes them)
+struct WorkCtr {
+  int next;       // next unclaimed work item beyond the statically assigned first wave
+  int done;       // warps that have left the launch
+  int q_count;    // refinement queue: problems the float32 pass did not bring to status 1
+  int q_pad;
+};
+
+// ===================================================================================================== handle
+#define MPCB200_HOST_STREAMS 4
+struct KernelPlan {     // launch shape of one kernel family (solve / refinement / closed loop) for this handle
+  int wpc;              // warps (= problems) per CTA
+  size_t smem;          // dynamic shared memory per CTA
+  int max_ctas;         // resident CTAs on the device (SM count x occupancy): the persistent grid never exceeds it
+};
+struct mpcb200_handle {
+  mpcb200_config cfg;
+  KernelPlan solve, refine, loop;
+  int words;            // slab words per problem
+  void* slab;           // global slab image [max_batch][words] (stepwise mode), allocated on first use
+  void* state;
+  void* obs_shift;
+  WorkCtr* ctr;         // device work counters (zeroed at create, self-resetting afterwards)
+  int* q_list;          // [max_batch] refinement queue (refine_f64 handles)
+  mpcb200_scenario* scn_table;   // device copy of the scenario table (mpcb200_set_scenarios)
+  int n_scn;
+  KernelPlan scn, scn_refine;    // launch shapes of the per-problem-scenario kernels (planned at set_scenarios)
+  KernelPlan forces, forces_refine;   // FORCESPRO-formulation kernels (planned at the first mpcb200_forces_solve)
+  int forces_planned;
+  size_t elem;          // sizeof(T)
+  int64_t launches;
+  // stepwise-mode context
+  const double* sw_xref;
+  int sw_B;
+  // host-path staging
+  double *d_xref, *d_X, *d_U;
+  int *d_status, *d_iters;
+  cudaStream_t hs[MPCB200_HOST_STREAMS];
+  int* h_pin;           // pinned host staging for status + iters (a pageable D2H target would serialise the chunk pipeline)
+  std::string err;
+};
+
+inline std::string& create_err() { static thread_local std::string e; return e; }
+
+inline int fail(mpcb200_handle* h, const char* what, cudaError_t e) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  if (h) h->err = buf; else create_err() = buf;
+  return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev; bool switched;
+  explicit DeviceGuard(int dev) : prev(-1), switched(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+inline int grid_for(const KernelPlan& k, int nwork) {
+  const int want = (nwork + k.wpc - 1) / k.wpc;
+  return want < k.max_ctas ? want : k.max_ctas;
+}
+
+// Opt every instantiation this handle can launch in to the device's FULL opt-in shared memory (a property of the function on
+// the device, shared by all handles: never a per-handle size, so one handle cannot lower another's limit), and ask the
+// occupancy calculator how many CTAs of the handle's size stay resident.
+template <typename K>
+inline cudaError_t plan_kernel(K kern, int wpc, size_t smem, int optin, int sms, int* max_ctas) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * wpc, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  *max_ctas = occ * sms;
+  return cudaSuccess;
+}

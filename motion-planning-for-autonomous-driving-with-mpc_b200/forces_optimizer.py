@@ -42,6 +42,9 @@ class B200ForcesproOptimizer(B200Optimizer):
     def __init__(self, configuration, init_values, predict_horizon, **kw):
         # optimizer.py:131: the friction row uses configuration.wheelbase
         kw.setdefault("l_fric", float(getattr(configuration, "wheelbase", 2.578)))
+        # the dynamics-curvature term of the Lagrangian Hessian is on by default: pure Gauss-Newton diverges on weight sets like
+        # USA_Lanker's (forces_core.cuh, backward_t); hessian="gn" selects the cheaper sweep where it is known to contract
+        kw.setdefault("hessian", "exact")
         super(B200ForcesproOptimizer, self).__init__(configuration, init_values, predict_horizon, **kw)
         w = self.weights_setting
         self.weights_terminal = np.array([float(w[k]) for k in _TERMINAL_KEYS])

@@ -123,8 +123,8 @@ static void forces_lane_body(int lane, void* arg) {
   for (int it = 0; it < J.cfg->max_iter && !st.done; ++it) {
     S.iterate(st);
     if (J.trace && lane == 0)
-      printf("it %3d mu %.2e step %.3e rho %.2e al %.3e ap %.3e ad %.3e c1 %.3e dphi %.3e status %d\n", st.iters, (double)st.mu,
-             (double)st.kkt, (double)st.rho, (double)st.d_al, (double)st.d_ap, (double)st.d_ad, (double)st.d_c1, (double)st.d_dphi, st.status);
+      printf("it %3d mu %.2e step %.3e rho %.2e al %.3e ap %.3e ad %.3e c1 %.3e dphi %.3e blk %d/%d status %d\n", st.iters, (double)st.mu,
+             (double)st.kkt, (double)st.rho, (double)st.d_al, (double)st.d_ap, (double)st.d_ad, (double)st.d_c1, (double)st.d_dphi, st.d_blk / 32, st.d_blk % 32, st.status);
   }
   S.store(J.xinit, J.par, J.Z);
   if (lane == 0) { J.status = st.status; J.iters = st.iters; }

@@ -39,6 +39,7 @@ def _problem(name, N, seed=None, B=1):
 def _emu_cfg(d, N, prec):
     cfg = hostsim.default_config(N, prec)
     cfg.Q[:] = list(d.Q); cfg.R[:] = list(d.R); cfg.r_sum = d.r_sum; cfg.dt = d.dt
+    cfg.hessian = 1            # dynamics-curvature term on: B200ForcesproOptimizer's default
     return cfg
 
 
@@ -160,7 +161,7 @@ def test_cuda_forces_solve_matches_oracle_and_emulator(name, N, B):
             worst = max(worst, np.abs(Z[b] - fn.split(d, r["w"])).max())
         assert worst < tol, (precision, worst)
         if precision == "f64":                                            # same source on the emulator: agreement to rounding of libm
-            Ze, ste, ite = hostsim.forces_solve(_emu_cfg(d0, N, 1), d0.Pt, x0[:2], P)
+            Ze, ste, ite = hostsim.forces_solve(_emu_cfg(d0, N, 1), d0.Pt, x0[:2], np.tile(P[None], (2, 1, 1)))
             assert np.abs(Ze - Z[:2]).max() < 1e-7 and list(ite) == list(it[:2])
 
 
