@@ -82,6 +82,70 @@ def _warm_one(args):
     return r["status"], float(np.abs(r["w"] - w).max()), clear
 
 
+def _forces_problem(name, N, B, seed):
+    """Synthetic batch of the FORCESPRO formulation: perturbed initial states + the parameters of closed-loop step 0."""
+    import mpc_b200
+    from mpc_b200.forces_optimizer import stage_parameters, velocity_profile
+    from mpc_b200.optimizer import obstacle_circles_and_radius
+    sc = mpc_b200.load_scenario(name)
+    circles, r_sum, off = obstacle_circles_and_radius(sc.static_obstacle)
+    x0 = mpc_b200.perturbed_initial_states(sc, B, seed, r_clear=r_sum + 0.05, obstacle_circles=circles, ego_offset=off)
+    P = stage_parameters(0, N, np.asarray(sc.reference_path, float)[:, :2], sc.orientation,
+                         velocity_profile(sc.iter_length, N, sc.desired_velocity), circles)
+    return sc, x0, P
+
+
+def _forces_oracle_one(args):
+    name, N, x0, P = args
+    import mpc_b200
+    from oracle import forces_nlp as fn, ipm
+    sc = mpc_b200.load_scenario(name)
+    d = fn.make_nlp(N, sc.dt, sc.weights_setting, x0, P, sc.static_obstacle)
+    r = ipm.solve(d, fn.initial_guess(d), model=fn)
+    return r["status"], r["w"]
+
+
+def _forces_extra_point(dev, args, torch, flush, cores, do_parity):
+    """`mpcb200_forces_solve` (the reference's FORCESPRO formulation): device-timed throughput + parity of a
+    bounded sample against the float64 oracle (oracle/forces_nlp.py + oracle/ipm.py)."""
+    from mpc_b200.forces_optimizer import B200ForcesproOptimizer
+    from mpc_b200.optimizer import make_configuration, init_values_from_state
+    name, N, B, seed = "ZAM_Over-1_1_LF", 30, 8192, 20261022
+    sc, x0, P = _forces_problem(name, N, B, seed)
+    opt = B200ForcesproOptimizer(make_configuration(sc, N, framework_name="forcespro"), init_values_from_state(sc.x0), N,
+                                 precision=args.precision, max_batch=B, device=dev.index)
+    xd = opt._dev(x0)
+    pd = opt._dev(P).unsqueeze(0).expand(B, N, 10).contiguous()
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        flush.fill_(1.0); Z, st, it = opt.forces_solve_batch(xd, pd)
+    torch.cuda.synchronize()
+    steps = 20
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s_, e_ in ev:
+        flush.fill_(1.0)
+        s_.record(stream); Z, st, it = opt.forces_solve_batch(xd, pd); e_.record(stream)
+    torch.cuda.synchronize()
+    ms = np.array([s_.elapsed_time(e_) for s_, e_ in ev])
+    Z, st, it = Z.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
+    out = {"workload": f"{name} FORCESPRO formulation (RK4, friction circle per stage, 9 circle pairs, terminal weights) batch={B} N={N} seed {seed} cold start",
+           "kernel": "mpc_forces_solve_kernel", "solves_per_s": B * steps / (ms.sum() * 1e-3), "ms_per_step": float(ms.mean()), "steps": steps,
+           "status_counts": {str(int(k)): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
+           "mean_sqp_iters": float(it.mean()), "max_sqp_iters": int(it.max())}
+    if do_parity:
+        from oracle import forces_nlp as fn
+        idx = np.linspace(0, B - 1, 2 * cores).astype(int)
+        with _pool(cores) as pool:
+            res = pool.map(_forces_oracle_one, [(name, N, x0[b], P) for b in idx], chunksize=1)
+        dz, n = 0.0, 0
+        for b, (so, w) in zip(idx, res):
+            if so == 1 and st[b] in (1, 3):
+                dz = max(dz, float(np.abs(w.reshape(N, 7) - Z[b]).max())); n += 1
+        out["parity"] = {"checked": n, "of": B, "sample": f"{len(idx)} evenly spaced instances", "max_abs_dz": dz, "tolerance": 1e-3,
+                         "against": "float64 oracle of the restated FORCESPRO-formulation NLP (stage functions pinned to the reference's generated C model)"}
+    return out
+
+
 def _pool(cores):
     import multiprocessing as mp
     return mp.get_context("fork").Pool(cores)
@@ -493,6 +557,7 @@ def run_product(args):
         del wl
         for key in EXTRA:
             extra[key] = _extra_point(key, dev, args, solver_opts, torch, flush, cores, do_parity=not args.no_cpu_baseline)
+        extra["forcespro_formulation"] = _forces_extra_point(dev, args, torch, flush, cores, do_parity=not args.no_cpu_baseline)
     nx, nu = 5 * (N + 1), 2 * N
     line = {
         "metric": METRIC, "value": world * B * steps / (total_ms * 1e-3), "unit": "solves/s", "n_gpus": world,

@@ -601,6 +601,9 @@ struct ForcesSolver {
     }
     w.sync();
   }
+  // (A second-order correction -- re-simulating the trial states from the trial inputs as warp_core.cuh does -- was built and
+  // measured: never accepted on the lane-following batches, no help on the crawling collision-avoidance instances (their l1
+  // infeasibility is in the circle-row slacks, not in the defects), +20 registers and -9 % throughput.  Not in the build.)
   MPC_HD bool trial_merit(const ProbState<T>& st, T al, T& dphi, T& c1, T& nz) const {
     const int N = P.N;
     const T mu = st.mu;

@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
 """Attribute executed warp instructions / stall samples of an ncu report to the solver PHASE (the call site inside
-WarpSolver::iterate()) using nvdisasm's inline chains.  Usage: ncu_by_phase.py <report.ncu-rep> <lib.so> <kernel-substr>"""
+WarpSolver::iterate() / ForcesSolver::iterate()) using nvdisasm's inline chains.
+Usage: ncu_by_phase.py <report.ncu-rep> <lib.so> <kernel-substr> [core header, default warp_core.cuh]"""
 import csv, re, subprocess, sys, collections, os, tempfile
 rep, so, kern = sys.argv[1:4]
+core_name = sys.argv[4] if len(sys.argv) > 4 else "warp_core.cuh"
 here = os.path.dirname(os.path.abspath(__file__))
-core = os.path.join(here, "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc", "warp_core.cuh")
+core = os.path.join(here, "..", "motion-planning-for-autonomous-driving-with-mpc_b200", "csrc", core_name)
 src = open(core).read().splitlines()
 it0 = next(i for i, l in enumerate(src) if "void iterate(" in l) + 1
 it1 = len(src)
@@ -28,7 +30,7 @@ for l in dis[start + 1:]:
         fresh = True
         phase = "kernel (I/O, init, loop)"
         for f, ln in chain:
-            if f == "warp_core.cuh" and it0 <= ln <= it1:
+            if f == core_name and it0 <= ln <= it1:
                 phase = f"iterate:{ln}  " + src[ln - 1].strip()[:70]
         leaf = chain[0] if chain else ("?", 0)
         info[int(m.group(1), 16)] = (phase, leaf, m.group(2).split()[0])
