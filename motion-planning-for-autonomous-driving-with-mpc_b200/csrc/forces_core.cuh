@@ -421,8 +421,10 @@ struct ForcesSolver {
   MPC_HD bool backward_t() const {
     const int N = P.N;
     T Pij = T(0);
-    T lam[5] = {T(0), T(0), T(0), T(0), T(0)};
+    T lam0 = T(0), lam1 = T(0), lam2 = T(0), lam3 = T(0), lam4 = T(0);       // lam_{k+1} (uniform)
     const T ownf = (T)tb.own;
+    bool pd = true;                                   // every input block so far positive definite (uniform; no early return:
+                                                      // a branch out of the loop would make every shuffle a guarded collective)
     for (int k = N - 1; k >= 0; --k) {
       const int o = L.o_rec + FREC * k;
       T b0[5], b1[5], q[5];
@@ -438,6 +440,9 @@ struct ForcesSolver {
       T F0j = sl[o + tb.so0], F1j = sl[o + tb.so1], F0i = T(0), F1i = sl[o + tb.si1];
       T G00 = sl[o + FR_RU], G01 = T(0), G11 = sl[o + FR_RU + 1];
       T Fxx = sl[o + tb.hidx];
+      T a_i[5];
+#pragma unroll
+      for (int l = 0; l < 5; ++l) a_i[l] = sl[o + tb.ai[l]];
 #pragma unroll
       for (int l = 0; l < 5; ++l) {
         const T mlj = w.shfl(M, 6 * l + tb.j), mli = w.shfl(M, 6 * l + tb.i);
@@ -445,12 +450,10 @@ struct ForcesSolver {
         F0j += b0[l] * mlj; F1j += b1[l] * mlj;
         F0i += b0[l] * mli; F1i += b1[l] * mli;
         G00 += b0[l] * mb0; G01 += b0[l] * mb1; G11 += b1[l] * mb1;
-        Fxx += sl[o + tb.ai[l]] * mlj;
+        Fxx += a_i[l] * mlj;
       }
       const T det = G00 * G11 - G01 * G01;
-      if (EX) {
-        if (!(G00 > T(0)) || !(det > T(1e-8) * G00 * G11)) return false;      // uniform across lanes
-      }
+      if (EX) pd = pd && (G00 > T(0)) && (det > T(1e-8) * G00 * G11);
       const T cdet = m_rcp(det);
       const T J00 = -cdet * G11, J01 = cdet * G01, J11 = -cdet * G00;
       const T T0 = J00 * F0j + J01 * F1j, T1 = J01 * F0j + J11 * F1j;      // gains [K | kff] column j
@@ -460,21 +463,14 @@ struct ForcesSolver {
         const T sn = sx(k, FS_TR), cs = sx(k, FS_TR + 1), tn = sx(k, FS_TR + 2);
         const T sec2 = T(1) + tn * tn;
         T ex = T(0);
-        if (tb.exw == 1) ex = -dt * v * (lam[0] * cs + lam[1] * sn);
-        if (tb.exw == 2) ex = dt * (lam[1] * cs - lam[0] * sn);
-        if (tb.exw == 3) ex = dt * lam[4] * T(2) * v * il * sec2 * tn;
-        if (tb.exw == 4) ex = dt * lam[4] * sec2 * il;
+        if (tb.exw == 1) ex = -dt * v * (lam0 * cs + lam1 * sn);
+        if (tb.exw == 2) ex = dt * (lam1 * cs - lam0 * sn);
+        if (tb.exw == 3) ex = dt * lam4 * T(2) * v * il * sec2 * tn;
+        if (tb.exw == 4) ex = dt * lam4 * sec2 * il;
         Fxx += ex;
-        T ln[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          T acc = sl[o + FR_LC + c];
-#pragma unroll
-          for (int l = 0; l < 5; ++l) acc += sl[o + FR_A + 5 * l + c] * lam[l];
-          ln[c] = acc;
-        }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) lam[c] = ln[c];
+        // lam_k: lane (i, .) forms component i from the A[l][i] it already holds, five broadcasts hand the vector to every lane
+        const T li = sl[o + FR_LC + tb.i] + (a_i[0] * lam0 + a_i[1] * lam1) + (a_i[2] * lam2 + a_i[3] * lam3) + a_i[4] * lam4;
+        lam0 = w.shfl(li, 0); lam1 = w.shfl(li, 6); lam2 = w.shfl(li, 12); lam3 = w.shfl(li, 18); lam4 = w.shfl(li, 24);
       }
       const T Pn = Fxx + F0i * T0 + F1i * T1;
       if (lane < 6) { sl[o + FR_KK + tb.j] = T0; sl[o + FR_KK + 6 + tb.j] = T1; }
@@ -482,10 +478,10 @@ struct ForcesSolver {
       Pij = Pn;
     }
     w.sync();
-    return true;
+    return pd;
   }
   MPC_HD void backward() const {
-    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; w.sync(); }
+    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; }
     backward_t<false>();
   }
 
