@@ -210,6 +210,15 @@ int mpcb200_forces_stage_eval(mpcb200_handle* h, const double* weights_terminal,
 int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, const double* d_xinit, const double* d_params,
                          const double* d_z_init, double* d_z, int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
+/* Road-boundary rows for `mpcb200_forces_solve` -- the six constraints per stage the reference states and leaves
+ * commented out (`find_closest_distance_with_road_boundary`, optimizer.py:18-30; rows :136-161 and :386-410, bounds :113-117,
+ * model.nh = 16 :208): for each of the three ego circle centres and each of the two boundaries, the distance to the CLOSEST
+ * VERTEX of the boundary polyline (`ca.mmin` over the vertex distances) >= r_min (radius_ego).  `left` / `right`: HOST pointers
+ * to [n][2] vertex lists in absolute coordinates (`configuration.left_road_boundary` / `right_road_boundary`,
+ * configuration.py:432-433); copied to the device.  n_left = n_right = 0 switches the rows off again (the default). */
+int mpcb200_forces_set_road_boundaries(mpcb200_handle* h, const double* left, int32_t n_left, const double* right, int32_t n_right,
+                                       double r_min);
+
 /* Introspection for benches/tests. */
 int64_t mpcb200_launch_count(const mpcb200_handle* h);       /* kernels launched by this handle so far */
 int32_t mpcb200_workspace_words(const mpcb200_handle* h);    /* words of the per-problem KKT slab */

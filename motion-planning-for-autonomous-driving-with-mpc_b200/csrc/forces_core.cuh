@@ -58,7 +58,9 @@ enum : int {
   FR_DU = 138,   // 2  step du_k
   FR_FAR = 140,  // 1  circle rows of x_k screened out this iteration
   FR_LC = 141,   // 5  multiplier-weighted gradient of the x_k terms (adjoint recursion of the dynamics-curvature term)
-  FREC = 147     // odd: lane = stage accesses are bank-conflict free
+  FR_BV = 146,   // 6  multipliers of the road-boundary rows: left boundary x (centre, front, rear circle), right boundary x (...)
+  FR_BS = 152,   // 6  their slacks
+  FREC = 159     // odd: lane = stage accesses are bank-conflict free
 };
 // state record k = 0..N-1
 enum : int {
@@ -73,8 +75,17 @@ enum : int {
 enum : int { FH00 = 0, FH01, FH04, FH11, FH14, FH44, FH22, FH23, FH33 };
 
 struct FLayout {
-  int N, o_state, o_rec, words;
-  MPC_HD explicit FLayout(int N_) : N(N_) { o_state = 0; o_rec = FST * N; words = (o_rec + FREC * N + 3) & ~3; }
+  int N, o_state, o_rec, o_misc, words;
+  // o_misc: 2 words, the position of xinit (the slab's positions are relative to it; the road boundaries are absolute)
+  MPC_HD explicit FLayout(int N_) : N(N_) { o_state = 0; o_rec = FST * N; o_misc = o_rec + FREC * N; words = (o_misc + 2 + 3) & ~3; }
+};
+
+// road boundaries (optional rows): vertex lists [n][2] in absolute coordinates, device memory
+template <typename T>
+struct RoadBounds {
+  const T* left; const T* right;
+  int nl, nr;
+  T r_min;          // radius_ego (optimizer.py:115)
 };
 
 template <typename T>
@@ -126,10 +137,12 @@ struct FLaneTab {
   }
 };
 
-template <typename T>
+// RB: the six road-boundary rows per stage are part of the problem (compile-time: a kernel without them carries none of their code)
+template <typename T, bool RB = false>
 struct ForcesSolver {
   const ParamsT<T>& P;
   const T* Pt;
+  const RoadBounds<T> rb;
   const FLayout L;
   const SlabRef<T> sl;
   const WarpCtx& w;
@@ -138,9 +151,9 @@ struct ForcesSolver {
   ForcesConsts<T> FC;
   const T a2max, r2, irows;
 
-  MPC_HD ForcesSolver(const FParams<T>& fp, const SlabRef<T>& slab, const WarpCtx& w_)
-      : P(fp.P), Pt(fp.Pt), L(fp.P.N), sl(slab), w(w_), lane(w_.lane()), tb(w_.lane()), a2max(fp.P.a_max * fp.P.a_max),
-        r2(fp.P.r_sum * fp.P.r_sum), irows(T(1) / T(18 * fp.P.N - 13)) {
+  MPC_HD ForcesSolver(const FParams<T>& fp, const SlabRef<T>& slab, const WarpCtx& w_, const RoadBounds<T>& rb_ = RoadBounds<T>{nullptr, nullptr, 0, 0, T(0)})
+      : P(fp.P), Pt(fp.Pt), rb(rb_), L(fp.P.N), sl(slab), w(w_), lane(w_.lane()), tb(w_.lane()), a2max(fp.P.a_max * fp.P.a_max),
+        r2(fp.P.r_sum * fp.P.r_sum), irows(T(1) / T(18 * fp.P.N - 13 + (RB ? 6 * (fp.P.N - 1) : 0))) {
     FC.dt = P.dt; FC.l_wb = P.l_wb; FC.l_fric = P.l_fric; FC.ego_off = P.ego_off;
     for (int q = 0; q < 5; ++q) { FC.Q[q] = P.Q[q]; FC.Pt[q] = fp.Pt[q]; }
     FC.R[0] = P.R[0]; FC.R[1] = P.R[1];
@@ -188,12 +201,40 @@ struct ForcesSolver {
     return dx * dx + dy * dy > reach * reach;
   }
 
+  // road-boundary row (side 0 left / 1 right, ego circle e): c = distance of the circle centre to the CLOSEST VERTEX of the
+  // boundary polyline - radius_ego >= 0 (find_closest_distance_with_road_boundary, optimizer.py:18-30: ca.mmin over the vertex
+  // distances; rows :156-161, bound :115).  Closest vertex by a coarse pass over every 8th vertex and a fine pass around the
+  // best one (road boundaries are smooth polylines with ~1 m spacing); the gradient is that of the distance to this vertex.
+  MPC_HD void brow(int side, int e, T px, T py, T sn, T cs, T& c, T& gx, T& gy, T& gp) const {
+    const T off = (e == 0) ? T(0) : (e == 1 ? P.ego_off : -P.ego_off);
+    const T ax = px + off * cs + sl[L.o_misc], ay = py + off * sn + sl[L.o_misc + 1];
+    const T* b = side ? rb.right : rb.left;
+    const int n = side ? rb.nr : rb.nl;
+    int best = 0; T bd = T(3e38);
+    for (int i = 0; i < n; i += 8) {
+      const T dx = ax - b[2 * i], dy = ay - b[2 * i + 1], d2 = dx * dx + dy * dy;
+      if (d2 < bd) { bd = d2; best = i; }
+    }
+    const int lo = best - 7 > 0 ? best - 7 : 0, hi = best + 7 < n - 1 ? best + 7 : n - 1;
+    for (int i = lo; i <= hi; ++i) {
+      const T dx = ax - b[2 * i], dy = ay - b[2 * i + 1], d2 = dx * dx + dy * dy;
+      if (d2 < bd) { bd = d2; best = i; }
+    }
+    const T dx = ax - b[2 * best], dy = ay - b[2 * best + 1];
+    const T d2 = m_max(dx * dx + dy * dy, T(1e-24));
+    const T ih = m_rsqrt(d2);
+    c = d2 * ih - rb.r_min;
+    gx = dx * ih; gy = dy * ih;
+    gp = off * (gy * cs - gx * sn);
+  }
+
   // ------------------------------------------------------------------ problem I/O (float64 arrays of ONE problem)
   // xinit [5]; params [N][10] (FORCESNLPsolver_params.all_parameters, stage major: path_x, path_y, v_des, psi_ref, 3 circle
   // centres); Zin [N][7] warm start (FORCESNLPsolver_params.x0; may be null: xinit tiled, zero inputs).  lane = stage.
   MPC_HD void load(const double* xinit, const double* par, const double* Zin) const {
     const int N = P.N;
     const double ox = xinit[0], oy = xinit[1];
+    if (lane == 0) { sl[L.o_misc] = (T)ox; sl[L.o_misc + 1] = (T)oy; }
     for (int k = lane; k < N; k += 32) {
       const double* p = par + 10 * k;
       const double ref[5] = {p[0], p[1], 0.0, p[2], p[3]};
@@ -279,6 +320,15 @@ struct ForcesSolver {
           rc(k, FR_V + FV_OB0 + 3 * e + o) = mu * m_rcp(s);
         }
       }
+      if (RB) {
+        for (int q = 0; q < 6; ++q) {
+          T c, gx, gy, gp; brow(q / 3, q % 3, xa[0], xa[1], sn, cs, c, gx, gy, gp);
+          if (k == 0 && c < -x0_tol()) bad = true;
+          const T s = m_max(c, kp * m_max(T(1), rb.r_min));
+          rc(k, FR_BS + q) = s;
+          rc(k, FR_BV + q) = mu * m_rcp(s);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 5; ++q) { rc(k, FR_DX + q) = T(0); sx(k, FS_XTT + q) = sx(k, FS_XT + q); }
       rc(k, FR_DU) = T(0); rc(k, FR_DU + 1) = T(0);
@@ -362,6 +412,21 @@ struct ForcesSolver {
               g[0] += cg * gx; g[1] += cg * gy; g[4] += cg * gp;
               lc[0] -= nu * gx; lc[1] -= nu * gy; lc[4] -= nu * gp;
             }
+          }
+        }
+        if (RB) {
+          for (int q = 0; q < 6; ++q) {
+            T c, gx, gy, gp; brow(q / 3, q % 3, xa[0], xa[1], sn, cs, c, gx, gy, gp);
+            T s = rc(k, FR_BS + q);
+            if (c > s) { s = c; rc(k, FR_BS + q) = s; }
+            const T nu = rc(k, FR_BV + q);
+            const T is = m_rcp(s);
+            const T wgt = nu * is, r = c - s;
+            const T cg = -(mu * is - wgt * r);
+            hd[0] += wgt * gx * gx; h01 += wgt * gx * gy; h04 += wgt * gx * gp;
+            hd[1] += wgt * gy * gy; h14 += wgt * gy * gp; hd[4] += wgt * gp * gp;
+            g[0] += cg * gx; g[1] += cg * gy; g[4] += cg * gp;
+            lc[0] -= nu * gx; lc[1] -= nu * gy; lc[4] -= nu * gp;
           }
         }
       }
@@ -565,6 +630,16 @@ struct ForcesSolver {
             }
           }
         }
+        if (RB) {
+          T sn, cs; m_sincos(xa[4], &sn, &cs);
+          for (int q = 0; q < 6; ++q) {
+            T c, gx, gy, gp; brow(q / 3, q % 3, xa[0], xa[1], sn, cs, c, gx, gy, gp);
+            const T s = rc(k, FR_BS + q);
+            const T r = c - s;
+            o.c1 += m_resid(r, c + rb.r_min);
+            row_limits(s, rc(k, FR_BV + q), gx * dx[0] + gy * dx[1] + gp * dx[4] + r, mu, o);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 5; ++q) o.step_inf = m_max(o.step_inf, m_abs(dx[q]));
       }
@@ -611,6 +686,7 @@ struct ForcesSolver {
       T rts[18];
 #pragma unroll
       for (int q = 0; q < 18; ++q) rts[q] = T(0);
+      T prodb = T(1), xsb = T(0);            // road-boundary rows: their (1 + x) product / log sum is accumulated in the loop
       if (k < N) {
         const bool term = (k == N - 1);
         const T u0 = rc(k, FR_U), u1 = rc(k, FR_U + 1);
@@ -666,6 +742,23 @@ struct ForcesSolver {
               }
             }
           }
+          if (RB) {
+            T sn, cs, snb, csb; m_sincos(xa[4], &sn, &cs); m_sincos(xba[4], &snb, &csb);
+            for (int q = 0; q < 6; ++q) {
+              T c, gx, gy, gp; brow(q / 3, q % 3, xa[0], xa[1], sn, cs, c, gx, gy, gp);
+              const T s = rc(k, FR_BS + q);
+              const T ds = al * (gx * rc(k, FR_DX) + gy * rc(k, FR_DX + 1) + gp * rc(k, FR_DX + 4) + (c - s));
+              {
+                const T x = ds * m_rcp(s);
+                ok = ok && (x > T(-1));
+                const T xc = m_max(x, T(-0.999999));
+                if (sizeof(T) == 4) { prodb += prodb * xc; xsb += m_abs(xc); }
+                else { const T l = m_log1p(xc); lg += l; lga += m_abs(l); }
+              }
+              T cb, g1, g2, g3; brow(q / 3, q % 3, xba[0], xba[1], snb, csb, cb, g1, g2, g3);
+              c1 += m_resid(cb - (s + ds), cb + rb.r_min);
+            }
+          }
         }
         rts[8] = al * dsf * m_rcp(sf);
         const Fric fb = fric(nu1, xba[2], xba[3]);
@@ -674,10 +767,10 @@ struct ForcesSolver {
       // two logarithms per stage: log of the product of the (1 + x_i) of the 9 bound / friction rows and of the 9 circle rows
       if (sizeof(T) == 4) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          T prod = T(1), xs = T(0);
+        for (int half = 0; half < (RB ? 3 : 2); ++half) {
+          T prod = (half == 2) ? prodb : T(1), xs = (half == 2) ? xsb : T(0);
 #pragma unroll
-          for (int q = 0; q < 9; ++q) {
+          for (int q = 0; q < (half == 2 ? 0 : 9); ++q) {
             const T x = rts[9 * half + q];
             ok = ok && (x > T(-1));
             const T xc = m_max(x, T(-0.999999));
@@ -758,6 +851,24 @@ struct ForcesSolver {
         } else {
           sum += T(9) * mu;
         }
+        if (RB) {
+          T sn, cs; m_sincos(xa[4], &sn, &cs);
+          for (int q = 0; q < 6; ++q) {
+            T c, gx, gy, gp; brow(q / 3, q % 3, xa[0], xa[1], sn, cs, c, gx, gy, gp);
+            const T s = rc(k, FR_BS + q);
+            const T ds = gx * dx[0] + gy * dx[1] + gp * dx[4] + (c - s);
+            const T snew = m_slack(s + al * ds);
+            // the boundary multipliers live outside FR_V: same update as upd()
+            const T nu = rc(k, FR_BV + q);
+            const T dnu = (mu - nu * s - nu * ds) * m_rcp(s);
+            T nn = m_max(nu + ad * dnu, T(1e-30));
+            nn = m_max(nn, mu * m_rcp(snew) * ikap);
+            rc(k, FR_BV + q) = nn;
+            const T cc = snew * nn; sum += cc; cmax = m_max(cmax, cc);
+            rc(k, FR_BS + q) = snew;
+            smin = m_min(smin, snew);
+          }
+        }
       }
       {
         const T snew = m_slack(sf + al * dsf);
@@ -837,6 +948,10 @@ struct ForcesSolver {
         for (int k = lane; k < P.N; k += 32) {
 #pragma unroll
           for (int q = 0; q < FNV; ++q) rc(k, FR_V + q) *= P.mu_up_factor;
+          if (RB) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) rc(k, FR_BV + q) *= P.mu_up_factor;
+          }
         }
         w.sync();
         return;

@@ -17,13 +17,14 @@ struct ForcesArgs {
   double* Z;             // [B][N][7]
   int* status; int* iters;
   WorkCtr* ctr; int* q_list;
+  RoadBounds<T> rb;      // road-boundary vertex lists (kernels instantiated with RB = true)
   int B, refine, dynamic, pdl_primary;
 };
 static size_t forces_smem_bytes_for(int N, int words, size_t elem, int wpc) {
   return (size_t)wpc * ((size_t)words * elem + (size_t)10 * N * sizeof(double));
 }
 
-template <typename T, int WPC>
+template <typename T, int WPC, bool RB>
 __global__ void __launch_bounds__(32 * WPC) mpc_forces_solve_kernel(const __grid_constant__ ForcesArgs<T> a) {
   unsigned char* const smem_raw = mpc_dyn_smem;
   __shared__ __align__(8) uint64_t bar_p[WPC];
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_forces_solve_kernel(const __grid
   if (a.pdl_primary) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (a.refine) asm volatile("griddepcontrol.wait;" ::: "memory");
   const WarpCtx w;
-  ForcesSolver<T> S(a.fp, SlabRef<T>{wid * L.words}, w);
+  ForcesSolver<T, RB> S(a.fp, SlabRef<T>{wid * L.words}, w, a.rb);
   const int nwork = a.refine ? a.ctr->q_count : a.B;
   uint32_t ph = 0;
   for (int item = blockIdx.x * WPC + wid; item < nwork;) {
@@ -89,10 +90,19 @@ __global__ void __launch_bounds__(32 * WPC) mpc_forces_solve_kernel(const __grid
 
 template <typename T>
 static cudaError_t plan_forces(KernelPlan& k, int optin, int sms) {
-  switch (k.wpc) {
-    case 2: return plan_kernel(mpc_forces_solve_kernel<T, 2>, 2, k.smem, optin, sms, &k.max_ctas);
-    default: k.wpc = 1; return plan_kernel(mpc_forces_solve_kernel<T, 1>, 1, k.smem, optin, sms, &k.max_ctas);
+  // one grid shape for the kernels with and without the road-boundary rows
+  int c0 = 0, c1 = 0;
+  cudaError_t e;
+  if (k.wpc == 2) {
+    e = plan_kernel(mpc_forces_solve_kernel<T, 2, false>, 2, k.smem, optin, sms, &c0);
+    if (e == cudaSuccess) e = plan_kernel(mpc_forces_solve_kernel<T, 2, true>, 2, k.smem, optin, sms, &c1);
+  } else {
+    k.wpc = 1;
+    e = plan_kernel(mpc_forces_solve_kernel<T, 1, false>, 1, k.smem, optin, sms, &c0);
+    if (e == cudaSuccess) e = plan_kernel(mpc_forces_solve_kernel<T, 1, true>, 1, k.smem, optin, sms, &c1);
   }
+  k.max_ctas = c0 < c1 ? c0 : c1;
+  return e;
 }
 template <typename T>
 static cudaError_t launch_forces(mpcb200_handle* h, ForcesArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
@@ -105,8 +115,9 @@ static cudaError_t launch_forces(mpcb200_handle* h, ForcesArgs<T>& a, cudaStream
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = a.refine ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (k.wpc == 2) return cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 2>, a);
-  return cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 1>, a);
+  const bool rb = a.rb.nl > 0 && a.rb.nr > 0;
+  if (k.wpc == 2) return rb ? cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 2, true>, a) : cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 2, false>, a);
+  return rb ? cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 1, true>, a) : cudaLaunchKernelEx(&cfg, mpc_forces_solve_kernel<T, 1, false>, a);
 }
 template <typename T>
 static void fill_forces_args(mpcb200_handle* h, ForcesArgs<T>& a, const double* wt, const double* xinit, const double* par, const double* Zin,
@@ -115,6 +126,10 @@ static void fill_forces_args(mpcb200_handle* h, ForcesArgs<T>& a, const double* 
   for (int i = 0; i < 5; ++i) a.fp.Pt[i] = (T)wt[i];
   a.xinit = xinit; a.par = par; a.Zin = Zin; a.Z = Z; a.status = status; a.iters = iters;
   a.ctr = h->ctr; a.q_list = nullptr; a.B = B; a.refine = 0; a.dynamic = 0; a.pdl_primary = 0;
+  const size_t nl = (size_t)h->rb_nl, nr = (size_t)h->rb_nr;
+  const T* base = (const T*)(sizeof(T) == 4 ? h->rb_f32 : h->rb_f64);         // [left (nl x 2) | right (nr x 2)]
+  a.rb.left = base; a.rb.right = base ? base + 2 * nl : nullptr;
+  a.rb.nl = base ? (int)nl : 0; a.rb.nr = base ? (int)nr : 0; a.rb.r_min = (T)h->rb_rmin;
 }
 static int ensure_forces_plan(mpcb200_handle* h) {
   if (h->forces_planned) return 0;
@@ -147,6 +162,29 @@ static int ensure_forces_plan(mpcb200_handle* h) {
 }
 
 extern "C" {
+
+int mpcb200_forces_set_road_boundaries(mpcb200_handle* h, const double* left, int32_t n_left, const double* right, int32_t n_right, double r_min) {
+  if (!h) return -2;
+  DeviceGuard guard(h->cfg.device);
+  cudaFree(h->rb_f32); cudaFree(h->rb_f64); h->rb_f32 = nullptr; h->rb_f64 = nullptr; h->rb_nl = h->rb_nr = 0;
+  if (n_left == 0 && n_right == 0) return 0;                            // rows off
+  if (!left || !right || n_left < 1 || n_right < 1 || n_left > 65536 || n_right > 65536 || !(r_min >= 0.0)) { h->err = "road boundaries: need two vertex lists of 1 .. 65536 points and r_min >= 0"; return -2; }
+  const size_t n = 2 * ((size_t)n_left + (size_t)n_right);
+  double* h64 = (double*)malloc(n * sizeof(double));
+  float* h32 = (float*)malloc(n * sizeof(float));
+  if (!h64 || !h32) { free(h64); free(h32); h->err = "out of host memory"; return -4; }
+  memcpy(h64, left, 2 * (size_t)n_left * sizeof(double));
+  memcpy(h64 + 2 * (size_t)n_left, right, 2 * (size_t)n_right * sizeof(double));
+  for (size_t i = 0; i < n; ++i) h32[i] = (float)h64[i];
+  cudaError_t e = cudaMalloc(&h->rb_f64, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->rb_f32, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->rb_f64, h64, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->rb_f32, h32, n * sizeof(float), cudaMemcpyHostToDevice);
+  free(h64); free(h32);
+  if (e != cudaSuccess) { cudaFree(h->rb_f32); cudaFree(h->rb_f64); h->rb_f32 = nullptr; h->rb_f64 = nullptr; return fail(h, "road boundaries upload", e); }
+  h->rb_nl = n_left; h->rb_nr = n_right; h->rb_rmin = r_min;
+  return 0;
+}
 
 int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, const double* d_xinit, const double* d_params, const double* d_z_init,
                          double* d_z, int32_t* d_status, int32_t* d_iters, int32_t B, void* stream) {

@@ -588,7 +588,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
   h = new (std::nothrow) mpcb200_handle();
   if (!h) { create_err() = "out of host memory"; return -4; }
   h->cfg = *cfg;
-  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr; h->ctr = nullptr; h->q_list = nullptr; h->scn_table = nullptr; h->n_scn = 0; h->forces_planned = 0;
+  h->launches = 0; h->slab = h->state = h->obs_shift = nullptr; h->ctr = nullptr; h->q_list = nullptr; h->scn_table = nullptr; h->n_scn = 0; h->forces_planned = 0; h->rb_f32 = h->rb_f64 = nullptr; h->rb_nl = h->rb_nr = 0; h->rb_rmin = 0.0;
   h->d_xref = h->d_X = h->d_U = nullptr; h->d_status = h->d_iters = nullptr; h->h_pin = nullptr;
   h->sw_xref = nullptr; h->sw_B = 0;
   const bool exact = cfg->hessian == MPCB200_HESS_EXACT;
@@ -626,7 +626,7 @@ int mpcb200_create(const mpcb200_config* cfg, mpcb200_handle** out) {
 void mpcb200_destroy(mpcb200_handle* h) {
   if (!h) return;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift); cudaFree(h->ctr); cudaFree(h->q_list); cudaFree(h->scn_table);
+  cudaFree(h->slab); cudaFree(h->state); cudaFree(h->obs_shift); cudaFree(h->ctr); cudaFree(h->q_list); cudaFree(h->scn_table); cudaFree(h->rb_f32); cudaFree(h->rb_f64);
   if (h->h_pin) for (int i = 0; i < MPCB200_HOST_STREAMS; ++i) cudaStreamDestroy(h->hs[i]);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaFree(h->d_xref); cudaFree(h->d_X); cudaFree(h->d_U); cudaFree(h->d_status); cudaFree(h->d_iters);

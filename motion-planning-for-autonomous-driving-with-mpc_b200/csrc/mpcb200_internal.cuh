@@ -73,6 +73,9 @@ struct mpcb200_handle {
   KernelPlan scn, scn_refine;    // launch shapes of the per-problem-scenario kernels (planned at set_scenarios)
   KernelPlan forces, forces_refine;   // FORCESPRO-formulation kernels (planned at the first mpcb200_forces_solve)
   int forces_planned;
+  void *rb_f32, *rb_f64;              // road-boundary vertex lists on the device, [left | right], both precisions (mpcb200_forces_set_road_boundaries)
+  int rb_nl, rb_nr;
+  double rb_rmin;
   size_t elem;          // sizeof(T)
   int64_t launches;
   // stepwise-mode context

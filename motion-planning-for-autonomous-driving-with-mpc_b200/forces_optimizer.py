@@ -52,6 +52,27 @@ class B200ForcesproOptimizer(B200Optimizer):
         self.vel_all = velocity_profile(int(self.iter_length), self.N, float(self.desired_velocity)) if self.iter_length >= self.N else \
             np.linspace(float(self.desired_velocity), 0, int(self.iter_length))
 
+    def set_road_boundaries(self, left=None, right=None, r_min=None):
+        """Switches the six road-boundary rows per stage on (the reference states them and leaves them commented out,
+        optimizer.py:18-30, 113-117, 136-161): each ego circle centre keeps at least `r_min` (default radius_ego, :115) from the
+        closest vertex of either boundary polyline.  left / right: [n,2] arrays (default: configuration.left_road_boundary /
+        right_road_boundary, configuration.py:432-433); `clear_road_boundaries()` switches the rows off."""
+        left = getattr(self.configuration, "left_road_boundary", None) if left is None else left
+        right = getattr(self.configuration, "right_road_boundary", None) if right is None else right
+        h = self.handle
+        if left is None or right is None:
+            h.check(h.lib.mpcb200_forces_set_road_boundaries(h.h, None, 0, None, 0, 0.0))
+            return
+        left = np.ascontiguousarray(left, np.float64).reshape(-1, 2)
+        right = np.ascontiguousarray(right, np.float64).reshape(-1, 2)
+        r_min = float(self.radius_ego if r_min is None else r_min)
+        h.check(h.lib.mpcb200_forces_set_road_boundaries(h.h, left.ctypes.data, len(left), right.ctypes.data, len(right), r_min))
+
+    def clear_road_boundaries(self):
+        """Road-boundary rows off again (the default, as in the reference where they are commented out)."""
+        h = self.handle
+        h.check(h.lib.mpcb200_forces_set_road_boundaries(h.h, None, 0, None, 0, 0.0))
+
     def _obstacle_within_reach(self):
         return True            # the friction circle is a nonlinear row at every stage: keep the float64 pass for float32 stragglers
 

@@ -488,7 +488,9 @@ def make_configuration(scenario, predict_horizon=None, framework_name="casadi", 
                            orientation=scenario.orientation, weights_setting=scenario.weights_setting,
                            static_obstacle=scenario.static_obstacle, noised=noised, use_case=scenario.use_case,
                            wheelbase=scenario.wheelbase, framework_name=framework_name,
-                           predict_horizon=predict_horizon, origin_reference_path=getattr(scenario, "origin_reference_path", None))
+                           predict_horizon=predict_horizon, origin_reference_path=getattr(scenario, "origin_reference_path", None),
+                           left_road_boundary=getattr(scenario, "left_road_boundary", None),
+                           right_road_boundary=getattr(scenario, "right_road_boundary", None))
 
 
 def init_values_from_state(x0):

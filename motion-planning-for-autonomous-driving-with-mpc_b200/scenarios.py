@@ -39,7 +39,9 @@ def load_scenario(name):
                            iter_length=int(d["iter_length"]), dt=float(d["dt"]), weights_setting=dict(d["weights_setting"]),
                            static_obstacle=dict(d["static_obstacle"]), use_case=d["use_case"],
                            wheelbase=float(d.get("wheelbase", 2.578)), synthesised=bool(d.get("synthesised", False)),
-                           origin_reference_path=(np.array(d["origin_reference_path"], float) if "origin_reference_path" in d else None))
+                           origin_reference_path=(np.array(d["origin_reference_path"], float) if "origin_reference_path" in d else None),
+                           left_road_boundary=(np.array(d["left_road_boundary"], float) if "left_road_boundary" in d else None),
+                           right_road_boundary=(np.array(d["right_road_boundary"], float) if "right_road_boundary" in d else None))
 
 
 def perturbed_initial_states(sc, B, seed, r_clear=None, obstacle_circles=None, ego_offset=0.75):

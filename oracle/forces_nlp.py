@@ -51,6 +51,15 @@ class ForcesData:
     l_wb: float = L_WB
     l_fric: float = L_FRICTION  # configuration.wheelbase (optimizer.py:131)
     veh: VehicleParams = field(default_factory=VehicleParams)
+    # road-boundary rows the reference left commented out (optimizer.py:18-30, 113-117, 136-161; model.nh = 16): the distance of
+    # each ego circle centre to the closest VERTEX of the left / right boundary polyline (ca.mmin over the vertices) >= radius_ego
+    left_boundary: np.ndarray = None     # (nl, 2)  configuration.left_road_boundary (configuration.py:432)
+    right_boundary: np.ndarray = None    # (nr, 2)  configuration.right_road_boundary (configuration.py:433)
+    r_ego: float = 1.2
+
+    @property
+    def nh(self):
+        return NH + (6 if self.left_boundary is not None else 0)
 
     @property
     def n(self):
@@ -58,7 +67,7 @@ class ForcesData:
 
     @property
     def m(self):
-        return NX + NX * (self.N - 1) + NH * self.N
+        return NX + NX * (self.N - 1) + self.nh * self.N
 
 
 # ------------------------------------------------------------------ stage functions (complex-safe, vectorised over rows)
@@ -88,6 +97,15 @@ def inequalities(d, z, p):
         ex, ey = z[..., 2] + o * c, z[..., 3] + o * s
         for j in range(3):
             out.append((ex - p[..., 4 + 2 * j]) ** 2 + (ey - p[..., 5 + 2 * j]) ** 2)
+    if d.left_boundary is not None:
+        # find_closest_distance_with_road_boundary (optimizer.py:18-30): min over the boundary VERTICES of the distance; rows in
+        # the reference's order: left boundary x (centre, front, rear), then right boundary (optimizer.py:156-161)
+        for bnd in (d.left_boundary, d.right_boundary):
+            for o in (0.0, d.ego_offset, -d.ego_offset):
+                ex, ey = z[..., 2] + o * c, z[..., 3] + o * s
+                dist = np.sqrt((ex[..., None] - bnd[:, 0]) ** 2 + (ey[..., None] - bnd[:, 1]) ** 2)
+                idx = np.argmin(dist.real, axis=-1)
+                out.append(np.take_along_axis(dist, idx[..., None], axis=-1)[..., 0])
     return np.stack(out, axis=-1)
 
 
@@ -149,8 +167,9 @@ def g_fun(d, w):
 
 def g_bounds(d):
     N, v = d.N, d.veh
-    hl = np.concatenate([[-INF], np.full(9, d.r_sum ** 2)])
-    hu = np.concatenate([[v.a_max ** 2], np.full(9, INF)])
+    nb = d.nh - NH
+    hl = np.concatenate([[-INF], np.full(9, d.r_sum ** 2), np.full(nb, d.r_ego)])          # optimizer.py:115-116 (commented): radius_ego
+    hu = np.concatenate([[v.a_max ** 2], np.full(9 + nb, INF)])
     lbg = np.concatenate([np.zeros(NX * N), np.tile(hl, N)])
     ubg = np.concatenate([np.zeros(NX * N), np.tile(hu, N)])
     lb = np.array([v.deltav_min, -v.a_max, -INF, -INF, v.delta_min, v.v_min, -INF])       # optimizer.py:108
@@ -175,13 +194,13 @@ def g_jac(d, w):
             for j in range(NZ):
                 if dc[k, i, j] != 0.0:
                     rows.append(r0 + i); cols.append(NZ * k + j); vals.append(-dc[k, i, j])
-    dh = _cjac(lambda q: inequalities(d, q, d.params), Z)  # (N, 10, 7)
+    dh = _cjac(lambda q: inequalities(d, q, d.params), Z)  # (N, nh, 7)
     r1 = NX * N
     for k in range(N):
-        for i in range(NH):
+        for i in range(d.nh):
             for j in range(NZ):
                 if dh[k, i, j] != 0.0:
-                    rows.append(r1 + NH * k + i); cols.append(NZ * k + j); vals.append(dh[k, i, j])
+                    rows.append(r1 + d.nh * k + i); cols.append(NZ * k + j); vals.append(dh[k, i, j])
     return sp.csr_matrix((vals, (rows, cols)), shape=(d.m, d.n))
 
 
@@ -193,7 +212,7 @@ def lag_hess(d, w, lam, sigma=1.0):
     t = _terminal(d)
     lam_dyn = np.zeros((N, NX))
     lam_dyn[:-1] = lam[NX:NX * N].reshape(N - 1, NX)
-    lam_h = lam[NX * N:].reshape(N, NH)
+    lam_h = lam[NX * N:].reshape(N, d.nh)
 
     def stage_lag(q):
         val = sigma * stage_cost(d, q, d.params, t) + np.sum(lam_h * inequalities(d, q, d.params), axis=-1)
@@ -226,7 +245,7 @@ def stage_parameters(k, N, path, orientation, vel_all, obstacle_centers):
                             np.asarray(orientation, float)[idx], np.tile(oc, (N, 1))])
 
 
-def make_nlp(N, dt, weights, xinit, params, static_obstacle, veh=None, wheelbase=L_FRICTION):
+def make_nlp(N, dt, weights, xinit, params, static_obstacle, veh=None, wheelbase=L_FRICTION, road_boundaries=None):
     veh = veh or VehicleParams()
     Q = np.array([weights["weight_x"], weights["weight_y"], weights["weight_steering_angle"], weights["weight_velocity"],
                   weights["weight_heading_angle"]], float)
@@ -237,7 +256,9 @@ def make_nlp(N, dt, weights, xinit, params, static_obstacle, veh=None, wheelbase
     r_ego, dd = compute_approximating_circle_radius(veh.length, veh.width)
     return ForcesData(N=N, dt=dt, Q=Q, R=R, Pt=Pt, xinit=np.asarray(xinit, float).reshape(NX),
                       params=np.asarray(params, float).reshape(N, NPAR), r_sum=r_ego + r_obs, ego_offset=dd / 4.0,
-                      l_fric=wheelbase, veh=veh)
+                      l_fric=wheelbase, veh=veh, r_ego=r_ego,
+                      left_boundary=None if road_boundaries is None else np.asarray(road_boundaries[0], float),
+                      right_boundary=None if road_boundaries is None else np.asarray(road_boundaries[1], float))
 
 
 def initial_guess(d, a0=0.0):

@@ -109,14 +109,15 @@ struct FJob {
   FParams<T> fp;
   T* slab;
   const double* xinit; const double* par; const double* Zin; double* Z;
+  RoadBounds<T> rb;
   HostWarp* hw;
   int status, iters, trace;
 };
-template <typename T>
+template <typename T, bool RB>
 static void forces_lane_body(int lane, void* arg) {
   FJob<T>& J = *(FJob<T>*)arg;
   WarpCtx w(J.hw, lane);
-  ForcesSolver<T> S(J.fp, SlabRef<T>{J.slab, 0}, w);
+  ForcesSolver<T, RB> S(J.fp, SlabRef<T>{J.slab, 0}, w, J.rb);
   S.load(J.xinit, J.par, J.Zin);
   ProbState<T> st;
   S.init(st);
@@ -131,10 +132,14 @@ static void forces_lane_body(int lane, void* arg) {
 }
 template <typename T>
 static void run_forces(const mpcb200_config& cfg, const double* Pt, const double* xinit, const double* par, const double* Zin, double* Z,
-                       int* status, int* iters, int B, int trace) {
+                       int* status, int* iters, int B, int trace, const double* bl = nullptr, int nl = 0, const double* br = nullptr, int nr = 0,
+                       double rmin = 0.0) {
   const int N = cfg.N;
   FLayout L(N);
   std::vector<T> buf(L.words + 4);
+  std::vector<T> bnd(2 * (size_t)(nl + nr) + 2);
+  for (int i = 0; i < 2 * nl; ++i) bnd[i] = (T)bl[i];
+  for (int i = 0; i < 2 * nr; ++i) bnd[2 * nl + i] = (T)br[i];
   HostWarp hw;
   for (int b = 0; b < B; ++b) {
     FJob<T> J;
@@ -142,8 +147,9 @@ static void run_forces(const mpcb200_config& cfg, const double* Pt, const double
     for (int i = 0; i < 5; ++i) J.fp.Pt[i] = (T)Pt[i];
     J.slab = buf.data(); J.xinit = xinit + 5 * (size_t)b; J.par = par + (size_t)b * 10 * N; J.Zin = Zin ? Zin + (size_t)b * 7 * N : nullptr;
     J.Z = Z + (size_t)b * 7 * N; J.hw = &hw; J.trace = trace; J.status = 0; J.iters = 0;
+    J.rb.left = bnd.data(); J.rb.right = bnd.data() + 2 * nl; J.rb.nl = nl; J.rb.nr = nr; J.rb.r_min = (T)rmin;
     for (auto& v : buf) v = T(NAN);
-    hw.run(&forces_lane_body<T>, &J);
+    if (nl > 0 && nr > 0) hw.run(&forces_lane_body<T, true>, &J); else hw.run(&forces_lane_body<T, false>, &J);
     if (status) status[b] = J.status;
     if (iters) iters[b] = J.iters;
   }
@@ -154,6 +160,12 @@ int hostsim_forces_solve(const mpcb200_config* cfg, const double* Pt, const doub
                          int* status, int* iters, int B, int trace) {
   if (cfg->precision == MPCB200_F64) run_forces<double>(*cfg, Pt, xinit, par, Zin, Z, status, iters, B, trace);
   else run_forces<float>(*cfg, Pt, xinit, par, Zin, Z, status, iters, B, trace);
+  return 0;
+}
+int hostsim_forces_solve_rb(const mpcb200_config* cfg, const double* Pt, const double* xinit, const double* par, const double* Zin, double* Z,
+                            int* status, int* iters, int B, int trace, const double* bl, int nl, const double* br, int nr, double rmin) {
+  if (cfg->precision == MPCB200_F64) run_forces<double>(*cfg, Pt, xinit, par, Zin, Z, status, iters, B, trace, bl, nl, br, nr, rmin);
+  else run_forces<float>(*cfg, Pt, xinit, par, Zin, Z, status, iters, B, trace, bl, nl, br, nr, rmin);
   return 0;
 }
 int hostsim_solve_dual(const mpcb200_config* cfg, const double* xref, double* X, double* U, double* lam, int* status, int* iters, int B) {

@@ -108,7 +108,7 @@ def solve_dual(cfg, xref, X, U, lam=None):
     return X, U, st, it, lam
 
 
-def forces_solve(cfg, weights_terminal, xinit, params, Zin=None, trace=0):
+def forces_solve(cfg, weights_terminal, xinit, params, Zin=None, trace=0, road_boundaries=None, r_min=1.2):
     """The FORCESPRO-formulation solver core (csrc/forces_core.cuh) on the emulator: xinit [B,5], params [B,N,10], optional warm
     start Zin [B,N,7] -> (Z [B,N,7], status, iters)."""
     xinit = np.ascontiguousarray(np.atleast_2d(xinit), np.float64)
@@ -120,5 +120,12 @@ def forces_solve(cfg, weights_terminal, xinit, params, Zin=None, trace=0):
     it = np.zeros(B, np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     zin = None if Zin is None else np.ascontiguousarray(Zin, np.float64)
-    lib().hostsim_forces_solve(C.byref(cfg), p(Pt), p(xinit), p(params), None if zin is None else p(zin), p(Z), p(st), p(it), B, trace)
+    if road_boundaries is None:
+        lib().hostsim_forces_solve(C.byref(cfg), p(Pt), p(xinit), p(params), None if zin is None else p(zin), p(Z), p(st), p(it), B, trace)
+    else:
+        bl = np.ascontiguousarray(road_boundaries[0], np.float64); br = np.ascontiguousarray(road_boundaries[1], np.float64)
+        f = lib().hostsim_forces_solve_rb
+        f.argtypes = [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double]
+        f(C.byref(cfg), p(Pt), p(xinit), p(params), None if zin is None else p(zin), p(Z), p(st), p(it), B, trace,
+          p(bl), len(bl), p(br), len(br), float(r_min))
     return Z, st, it

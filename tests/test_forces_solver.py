@@ -127,6 +127,39 @@ def test_emulated_core_warm_start_and_infeasible_start():
     assert st3[0] == -8
 
 
+def _rb_problem(N, shift=-1.5):
+    """Lane following with the reference path pushed 1.5 m towards the right road boundary: the boundary rows become active."""
+    sc, d0, P, x0 = _problem("ZAM_Over-1_1_LF", N)
+    P = P.copy(); P[:, 1] += shift
+    rb = (sc.left_road_boundary, sc.right_road_boundary)
+    d = fn.make_nlp(N, sc.dt, sc.weights_setting, x0[0], P, sc.static_obstacle, road_boundaries=rb)
+    return sc, d, P, x0, rb
+
+
+def test_road_boundaries_are_the_reference_lanelet_bounds():
+    """configuration.py:432-433: right vertices of the network's 2nd / 1st lanelet (201 vertices each on ZAM_Over-1_1)."""
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    L, R = sc.left_road_boundary, sc.right_road_boundary
+    assert L.shape == (201, 2) and R.shape == (201, 2)
+    assert np.allclose(R[0], [0.0, -3.25]) and np.allclose(L[-1], [0.0, 3.25])       # a 6.5 m wide road around the x axis at its start
+    assert mpc_b200.load_scenario("USA_Lanker-2_18_T-1_LF").left_road_boundary is None  # the hard-wired lanelet indices only mean something on ZAM_Over
+
+
+def test_emulated_core_road_boundary_rows_match_the_oracle():
+    """min-over-vertices distance rows (optimizer.py:18-30, 136-161), active on this instance; == oracle."""
+    sc, d, P, x0, rb = _rb_problem(10)
+    r = ipm.solve(d, fn.initial_guess(d), model=fn)
+    assert r["status"] == 1
+    Zo = fn.split(d, r["w"])
+    assert abs(fn.inequalities(d, Zo, P)[:, 10:].min() - d.r_ego) < 1e-8            # a boundary row is active at the optimum
+    for prec, tol in ((1, TOL64), (0, TOL32)):
+        Z, st, it = hostsim.forces_solve(_emu_cfg(d, 10, prec), d.Pt, x0, P, road_boundaries=rb, r_min=d.r_ego)
+        assert st[0] in (1, 3) and np.abs(Z[0] - Zo).max() < tol, (prec, st, np.abs(Z[0] - Zo).max())
+        assert fn.inequalities(d, Z[0], P)[:, 10:].min() > d.r_ego - tol
+    Zn, _, _ = hostsim.forces_solve(_emu_cfg(d, 10, 1), d.Pt, x0, P)                 # rows off: the ego cuts through the margin
+    assert fn.inequalities(d, Zn[0], P)[:, 10:].min() < 0.5
+
+
 # ----------------------------------------------------------------------------------------------------------------- GPU
 def _gpu_opt(sc, N, precision, **kw):
     from mpc_b200.optimizer import make_configuration, init_values_from_state
@@ -207,3 +240,29 @@ def test_cuda_forcespro_optimizer_closed_loop_contract():
     _, d0, P, x0 = _problem("ZAM_Over-1_1_LF", 10)
     d, r = _oracle(d0, x[0])
     assert np.abs(u[0] - fn.split(d, r["w"])[0, :2]).max() < TOL32
+
+
+@pytest.mark.gpu
+def test_cuda_road_boundary_rows_match_the_oracle_and_switch_off():
+    """`mpcb200_forces_set_road_boundaries`: active boundary rows on the GPU == oracle; switching them off restores the plain solve."""
+    N = 10
+    sc, d, P, x0, rb = _rb_problem(N)
+    r = ipm.solve(d, fn.initial_guess(d), model=fn)
+    Zo = fn.split(d, r["w"])
+    rng = np.random.default_rng(3)
+    xb = x0 + rng.normal(size=(33, 5)) * np.array([0.3, 0.1, 0.005, 0.5, 0.01])      # a ragged batch around the nominal start; row 0 = nominal
+    xb[0] = x0[0]
+    for precision, tol in (("f64", TOL64), ("f32", TOL32)):
+        opt = _gpu_opt(sc, N, precision, max_batch=64)
+        Z0, st0, _ = opt.forces_solve_batch(xb, P)
+        opt.set_road_boundaries()                                                    # the configuration's boundaries, r_min = radius_ego
+        Z, st, it = opt.forces_solve_batch(xb, P)
+        Zc, stc = Z.cpu().numpy(), st.cpu().numpy()
+        assert np.isin(stc, (1, 3)).all(), stc
+        assert np.abs(Zc[0] - Zo).max() < tol, (precision, np.abs(Zc[0] - Zo).max())
+        for b in range(len(xb)):
+            assert fn.inequalities(d, Zc[b], P)[1:, 10:].min() > d.r_ego - 2 * tol     # every instance keeps the margin (stage 0 is given)
+        assert fn.inequalities(d, Z0.cpu().numpy()[0], P)[:, 10:].min() < 0.5         # ... which the plain solve does not
+        opt.clear_road_boundaries()
+        Z1, st1, _ = opt.forces_solve_batch(xb, P)
+        assert (Z1 - Z0).abs().max() == 0.0                                           # rows off again: bit-identical to the first solve

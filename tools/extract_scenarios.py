@@ -321,7 +321,13 @@ def build(name, xml, yaml_rel, use_case, synth=False):
                         orientation=ob["orientation"])
     else:  # configuration.py:477-483
         obstacle = dict(position_x=-100.0, position_y=0.0, length=0.0, width=0.0, orientation=0.0)
-    return dict(name=name, xml=xml, use_case=use_case, synthesised=synth, dt=dt,
+    # road boundaries as Configuration sets them (configuration.py:432-433): the RIGHT vertices of the 2nd and of the 1st lanelet
+    # of the network (hard-wired indices in the reference: meaningful for the two-lanelet ZAM_Over road only)
+    lids = list(sc["lanelets"].keys())
+    bounds = {}
+    if len(lids) == 2:
+        bounds = dict(left_road_boundary=sc["lanelets"][lids[1]]["right"].tolist(), right_road_boundary=sc["lanelets"][lids[0]]["right"].tolist())
+    return dict(**bounds, name=name, xml=xml, use_case=use_case, synthesised=synth, dt=dt,
                 x0=[sc["init"]["x"], sc["init"]["y"], 0.0, sc["init"]["v"], sc["init"]["psi"]],
                 route_lanelets=chain, desired_velocity=v_des, iter_length=int(path.shape[0]),
                 origin_reference_path=origin.tolist(),
