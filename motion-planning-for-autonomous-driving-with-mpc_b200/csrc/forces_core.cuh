@@ -901,6 +901,10 @@ struct ForcesSolver {
     if (f.c1 > T(8) * epsm * f.mag) {
       const T need = f.dphi * m_rcp(T(0.5) * f.c1);
       if (need > st.rho) st.rho = need * T(1.5) + T(1);
+      // the penalty parameter also comes DOWN again when the current step needs much less: one huge early step (a blocked
+      // iterate far from the central path) otherwise leaves rho in the thousands, and every later step that bends the trajectory
+      // around an obstacle is cut to 1/16 .. 1/32 by the l1 merit (measured: collision avoidance / road-boundary crawlers)
+      else if (rho_decay() && need * T(1.5) + T(1) < T(0.5) * st.rho) st.rho = m_max(T(1), m_max(need * T(1.5) + T(1), T(0.5) * st.rho));
     }
     const T slope = f.dphi - st.rho * f.c1;
     const T cfloor = T(8) * epsm * f.mag;
@@ -968,6 +972,14 @@ struct ForcesSolver {
       if (mu_new < st.mu) st.rho = m_max(T(1), st.rho * T(0.5));
       st.mu = mu_new;
     }
+  }
+  MPC_HD static bool rho_decay() {
+#if !defined(__CUDACC__) && defined(MPC_DIAG)
+    static const bool v = getenv("FORCES_RHO_DECAY") ? atoi(getenv("FORCES_RHO_DECAY")) != 0 : true;
+    return v;
+#else
+    return true;
+#endif
   }
   MPC_HD static T mu_feas() {
 #if !defined(__CUDACC__) && defined(MPC_DIAG)
