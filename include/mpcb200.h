@@ -210,6 +210,18 @@ int mpcb200_forces_stage_eval(mpcb200_handle* h, const double* weights_terminal,
 int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, const double* d_xinit, const double* d_params,
                          const double* d_z_init, double* d_z, int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
 
+/* ForcesproOptimizer.optimize()'s receding-horizon loop (optimizer.py:286-362) for B egos in ONE launch, one ego per warp: per
+ * closed-loop step k the `all_parameters` rows are built on the device (path points / headings k+1 .. k+N replenished with the
+ * last one, :296-311; `d_velocity` [iter_length] is the desired-velocity profile of :291-294; the handle's obstacle circles tiled,
+ * :306-317), the NLP is solved (warm start: the previous solution shifted one stage), the first input is applied to the RK4
+ * plant in float64 (model.eq, :359).  d_x0 [B][5] -> d_traj [B][iter_length][5] (state at the start of each step, the reference's
+ * `x` without its last column, :366), d_ctrl [B][iter_length][2], d_status / d_iters [B][iter_length].  Noise-free loop (the
+ * `noised` option of :347-356 stays on the host: B200ForcesproOptimizer.optimize_batch).  No float64 refinement pass inside
+ * the loop: a float32 handle reports status 3 where it stalls. */
+int mpcb200_forces_closed_loop(mpcb200_handle* h, const double* weights_terminal, int32_t iter_length, const double* d_path,
+                               const double* d_orientation, const double* d_velocity, const double* d_x0, double* d_traj, double* d_ctrl,
+                               int32_t* d_status, int32_t* d_iters, int32_t B, void* cuda_stream);
+
 /* Road-boundary rows for `mpcb200_forces_solve` -- the six constraints per stage the reference states and leaves
  * commented out (`find_closest_distance_with_road_boundary`, optimizer.py:18-30; rows :136-161 and :386-410, bounds :113-117,
  * model.nh = 16 :208): for each of the three ego circle centres and each of the two boundaries, the distance to the CLOSEST

@@ -62,6 +62,7 @@ EXPORTS = {
     "mpcb200_forces_stage_eval": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mpcb200_forces_solve": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)] + [C.c_void_p] * 6 + [C.c_int32, C.c_void_p]),
     "mpcb200_forces_set_road_boundaries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double]),
+    "mpcb200_forces_closed_loop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_void_p]),
     "mpcb200_launch_count": (C.c_int64, [C.c_void_p]),
     "mpcb200_workspace_words": (C.c_int32, [C.c_void_p]),
     "mpcb200_slab_in_smem": (C.c_int32, [C.c_void_p]),

@@ -88,6 +88,108 @@ __global__ void __launch_bounds__(32 * WPC) mpc_forces_solve_kernel(const __grid
   }
 }
 
+// ===================================================================================================== closed loop
+// ForcesproOptimizer.optimize()'s loop (optimizer.py:286-362) for one ego per warp, no host round trip between the MPC steps: the
+// parameter rows of step k (next N path points / headings replenished with the last one, the desired-velocity profile, the obstacle
+// circle centres tiled, :288-317), one solve (warm start = the previous solution shifted one stage), the first input applied to
+// the RK4 plant in float64 (model.eq, :359).  Shared memory per warp: the KKT slab + float64 parameter block [N][10] + stage
+// variables [N][7] + xinit.
+template <typename T>
+struct ForcesLoopArgs {
+  FParams<T> fp;
+  RoadBounds<T> rb;
+  double obstacle[6];
+  const double* path;     // [Tlen][2]
+  const double* orient;   // [Tlen]
+  const double* vel;      // [Tlen] desired-velocity profile (optimizer.py:291-294)
+  const double* x0;       // [B][5]
+  double* traj;           // [B][Tlen][5]
+  double* ctrl;           // [B][Tlen][2]
+  int* status; int* iters;   // [B][Tlen]
+  WorkCtr* ctr;
+  double l_wb, dt;
+  int B, Tlen, dynamic;
+};
+static size_t forces_loop_smem_bytes_for(int N, int words, size_t elem, int wpc) {
+  return (size_t)wpc * ((size_t)words * elem + (size_t)(17 * N + 6) * sizeof(double));
+}
+__device__ __forceinline__ void ks_rhs_f64(const double* x, double u0, double u1, double l_wb, double* f) {
+  double s, c; sincos(x[4], &s, &c);
+  f[0] = x[3] * c; f[1] = x[3] * s; f[2] = u0; f[3] = u1; f[4] = x[3] / l_wb * tan(x[2]);
+}
+
+template <typename T, int WPC, bool RB>
+__global__ void __launch_bounds__(32 * WPC) mpc_forces_closed_loop_kernel(const __grid_constant__ ForcesLoopArgs<T> a) {
+  unsigned char* const smem_raw = mpc_dyn_smem;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.fp.P.N, Tlen = a.Tlen;
+  const FLayout L(N);
+  const int total_warps = gridDim.x * WPC;
+  double* const par = reinterpret_cast<double*>(smem_raw + (size_t)WPC * L.words * sizeof(T)) + (size_t)wid * (17 * N + 6);
+  double* const Zw = par + 10 * N;
+  double* const xs = Zw + 7 * N;         // xinit of the current step
+  const WarpCtx w;
+  ForcesSolver<T, RB> S(a.fp, SlabRef<T>{wid * L.words}, w, a.rb);
+  for (int b = blockIdx.x * WPC + wid; b < a.B;) {
+    double x[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) x[j] = a.x0[(size_t)b * 5 + j];
+    for (int k = 0; k < Tlen; ++k) {
+      __syncwarp();
+      if (lane < 5) { xs[lane] = x[lane]; a.traj[((size_t)b * Tlen + k) * 5 + lane] = x[lane]; }
+      for (int j = lane; j < N; j += 32) {
+        const int idx = (k + 1 + j < Tlen) ? (k + 1 + j) : (Tlen - 1);
+        double* p = par + 10 * j;
+        p[0] = a.path[2 * idx]; p[1] = a.path[2 * idx + 1]; p[2] = a.vel[idx]; p[3] = a.orient[idx];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) p[4 + q] = a.obstacle[q];
+      }
+      __syncwarp();
+      ProbState<T> st;
+      S.load(xs, par, k > 0 ? Zw : nullptr);
+      S.init(st);
+      for (int it = 0; it < a.fp.P.max_iter && !st.done; ++it) S.iterate(st);
+      S.store(xs, par, Zw);
+      const double u0 = Zw[0], u1 = Zw[1];
+      if (lane == 0) {
+        a.ctrl[((size_t)b * Tlen + k) * 2] = u0; a.ctrl[((size_t)b * Tlen + k) * 2 + 1] = u1;
+        a.status[(size_t)b * Tlen + k] = st.status; a.iters[(size_t)b * Tlen + k] = st.iters;
+      }
+      // plant: one RK4 step in float64 (every lane redundantly)
+      {
+        const double h = a.dt;
+        double k1[5], k2[5], k3[5], k4[5], t[5];
+        ks_rhs_f64(x, u0, u1, a.l_wb, k1);
+        for (int j = 0; j < 5; ++j) t[j] = x[j] + 0.5 * h * k1[j];
+        ks_rhs_f64(t, u0, u1, a.l_wb, k2);
+        for (int j = 0; j < 5; ++j) t[j] = x[j] + 0.5 * h * k2[j];
+        ks_rhs_f64(t, u0, u1, a.l_wb, k3);
+        for (int j = 0; j < 5; ++j) t[j] = x[j] + h * k3[j];
+        ks_rhs_f64(t, u0, u1, a.l_wb, k4);
+        for (int j = 0; j < 5; ++j) x[j] += h / 6.0 * (k1[j] + 2.0 * k2[j] + 2.0 * k3[j] + k4[j]);
+      }
+      // warm start of the next step: the solution shifted one stage, the last stage repeated
+      __syncwarp();
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        double z[7];
+        if (j < N) { const int src = (j + 1 < N) ? j + 1 : N - 1; for (int q = 0; q < 7; ++q) z[q] = Zw[7 * src + q]; }
+        __syncwarp();
+        if (j < N) { for (int q = 0; q < 7; ++q) Zw[7 * j + q] = z[q]; }
+        __syncwarp();
+      }
+    }
+    if (!a.dynamic) break;
+    int nxt = 0;
+    if (lane == 0) nxt = total_warps + atomicAdd(&a.ctr->next, 1);
+    b = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+  if (a.dynamic && lane == 0) {
+    __threadfence();
+    if (atomicAdd(&a.ctr->done, 1) == total_warps - 1) { a.ctr->next = 0; a.ctr->done = 0; }
+  }
+}
+
 template <typename T>
 static cudaError_t plan_forces(KernelPlan& k, int optin, int sms) {
   // one grid shape for the kernels with and without the road-boundary rows
@@ -161,6 +263,36 @@ static int ensure_forces_plan(mpcb200_handle* h) {
   return 0;
 }
 
+template <typename T>
+static int forces_closed_loop_t(mpcb200_handle* h, const double* wt, int32_t Tlen, const double* d_path, const double* d_orient, const double* d_vel,
+                                const double* d_x0, double* d_traj, double* d_ctrl, int32_t* d_status, int32_t* d_iters, int32_t B, cudaStream_t s) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+  const int optin = (int)prop.sharedMemPerBlockOptin, sms = prop.multiProcessorCount;
+  const FLayout L(h->cfg.N);
+  const size_t smem = forces_loop_smem_bytes_for(h->cfg.N, L.words, sizeof(T), 1);
+  if (smem + 1024 > prop.sharedMemPerBlockOptin) { h->err = "horizon too long for the FORCESPRO-formulation closed loop"; return -2; }
+  ForcesLoopArgs<T> a;
+  ForcesArgs<T> tmp; fill_forces_args(h, tmp, wt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B);
+  a.fp = tmp.fp; a.rb = tmp.rb;
+  for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
+  a.path = d_path; a.orient = d_orient; a.vel = d_vel; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
+  a.ctr = h->ctr; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = Tlen;
+  const bool rb = a.rb.nl > 0 && a.rb.nr > 0;
+  int max_ctas = 0;
+  cudaError_t e = rb ? plan_kernel(mpc_forces_closed_loop_kernel<T, 1, true>, 1, smem, optin, sms, &max_ctas)
+                     : plan_kernel(mpc_forces_closed_loop_kernel<T, 1, false>, 1, smem, optin, sms, &max_ctas);
+  if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO-formulation closed loop)", e);
+  const int ctas = B < max_ctas ? B : max_ctas;
+  a.dynamic = (B > ctas) ? 1 : 0;
+  if (rb) mpc_forces_closed_loop_kernel<T, 1, true><<<ctas, 32, smem, s>>>(a);
+  else mpc_forces_closed_loop_kernel<T, 1, false><<<ctas, 32, smem, s>>>(a);
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, "mpc_forces_closed_loop_kernel launch", e);
+  return 0;
+}
+
 extern "C" {
 
 int mpcb200_forces_set_road_boundaries(mpcb200_handle* h, const double* left, int32_t n_left, const double* right, int32_t n_right, double r_min) {
@@ -214,6 +346,19 @@ int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, cons
   }
   if (e != cudaSuccess) return fail(h, "mpc_forces_solve_kernel launch", e);
   return 0;
+}
+
+int mpcb200_forces_closed_loop(mpcb200_handle* h, const double* weights_terminal, int32_t iter_length, const double* d_path, const double* d_orientation,
+                               const double* d_velocity, const double* d_x0, double* d_traj, double* d_ctrl, int32_t* d_status, int32_t* d_iters,
+                               int32_t B, void* stream) {
+  if (!h) return -2;
+  if (B <= 0) return 0;
+  if (B > h->cfg.max_batch) { h->err = "B exceeds cfg.max_batch"; return -2; }
+  if (!weights_terminal || !d_path || !d_orientation || !d_velocity || !d_x0 || !d_traj || !d_ctrl || !d_status || !d_iters || iter_length < 1) { h->err = "null argument"; return -2; }
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.precision == MPCB200_F64) return forces_closed_loop_t<double>(h, weights_terminal, iter_length, d_path, d_orientation, d_velocity, d_x0, d_traj, d_ctrl, d_status, d_iters, B, s);
+  return forces_closed_loop_t<float>(h, weights_terminal, iter_length, d_path, d_orientation, d_velocity, d_x0, d_traj, d_ctrl, d_status, d_iters, B, s);
 }
 
 }  // extern "C"

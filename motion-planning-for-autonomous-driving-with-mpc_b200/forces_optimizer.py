@@ -111,20 +111,39 @@ class B200ForcesproOptimizer(B200Optimizer):
         k1 = f(x); k2 = f(x + 0.5 * h * k1); k3 = f(x + 0.5 * h * k2); k4 = f(x + h * k3)
         return x + h / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
 
-    def optimize_batch(self, x0, warm_start=True, return_device=False):
+    def optimize_batch(self, x0, warm_start=True, return_device=False, on_device=None):
         """ForcesproOptimizer.optimize()'s loop (optimizer.py:286-362) for B egos: per closed-loop step the parameters of the next N
         path points, one solve, the first input applied to the RK4 plant.  x0 [B,5] -> (states[B,T,5], inputs[B,T,2], status[B,T],
         iters[B,T]).  warm_start: the previous solution shifted one stage is the next initial guess (the reference re-uses its
-        step-0 guess every step, optimizer.py:267-277; the converged optimum does not depend on it)."""
+        step-0 guess every step, optimizer.py:267-277; the converged optimum does not depend on it).
+        on_device (default: True for noise-free runs): the whole loop in ONE launch (`mpcb200_forces_closed_loop`); otherwise one
+        `mpcb200_forces_solve` per step driven from here (needed for `configuration.noised`)."""
         t = self.torch
         x = self._dev(x0).reshape(-1, 5).clone()
         B, T = x.shape[0], int(self.iter_length)
+        noised = bool(getattr(self.configuration, "noised", False))
+        if on_device is None:
+            on_device = not noised and warm_start
+        if on_device:
+            if noised:
+                raise ValueError("the device loop is noise-free; use on_device=False for configuration.noised")
+            path, orient = self._path_tensors()
+            vel = self._dev(np.asarray(self.vel_all, float)[np.minimum(np.arange(T), len(self.vel_all) - 1)])
+            traj = t.empty(B, T, 5, dtype=t.float64, device=self.device)
+            ctrl = t.empty(B, T, 2, dtype=t.float64, device=self.device)
+            status = t.empty(B, T, dtype=t.int32, device=self.device)
+            iters = t.empty(B, T, dtype=t.int32, device=self.device)
+            h = self.handle
+            h.check(h.lib.mpcb200_forces_closed_loop(h.h, self._wt, T, path.data_ptr(), orient.data_ptr(), vel.data_ptr(), x.data_ptr(),
+                                                     traj.data_ptr(), ctrl.data_ptr(), status.data_ptr(), iters.data_ptr(), B, self._stream()))
+            if return_device:
+                return traj, ctrl, status, iters
+            return traj.cpu().numpy(), ctrl.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
         traj = t.empty(B, T, 5, dtype=t.float64, device=self.device)
         ctrl = t.empty(B, T, 2, dtype=t.float64, device=self.device)
         status = t.empty(B, T, dtype=t.int32, device=self.device)
         iters = t.empty(B, T, dtype=t.int32, device=self.device)
         Z = None
-        noised = bool(getattr(self.configuration, "noised", False))
         for k in range(T):
             traj[:, k] = x
             zin = None

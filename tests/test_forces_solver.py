@@ -266,3 +266,21 @@ def test_cuda_road_boundary_rows_match_the_oracle_and_switch_off():
         opt.clear_road_boundaries()
         Z1, st1, _ = opt.forces_solve_batch(xb, P)
         assert (Z1 - Z0).abs().max() == 0.0                                           # rows off again: bit-identical to the first solve
+
+
+@pytest.mark.gpu
+def test_cuda_forces_closed_loop_on_device_equals_the_host_driven_loop():
+    """`mpcb200_forces_closed_loop` (one launch, one ego per warp) == one `mpcb200_forces_solve` per step driven from Python."""
+    sc = mpc_b200.load_scenario("ZAM_Over-1_1_LF")
+    rng = np.random.default_rng(11)
+    x0 = sc.x0[None, :] + rng.normal(size=(37, 5)) * np.array([0.3, 0.2, 0.005, 0.5, 0.02])
+    x0[:, 2] = 0.0
+    opt = _gpu_opt(sc, 10, "f64", max_batch=64)
+    td, cd, sd, itd = opt.optimize_batch(x0, on_device=True)
+    th, ch, sh, ith = opt.optimize_batch(x0, on_device=False)
+    assert (sd == 1).all() and (sh == 1).all()
+    assert np.abs(td - th).max() < 1e-6 and np.abs(cd - ch).max() < 1e-6
+    assert np.array_equal(td[:, 0], x0)
+    o32 = _gpu_opt(sc, 10, "f32", max_batch=64)
+    t32, c32, s32, _ = o32.optimize_batch(x0)                       # float32 device loop (default route)
+    assert np.isin(s32, (1, 3)).all() and np.abs(c32 - ch).max() < 5e-3 and np.abs(t32 - th).max() < 5e-3
