@@ -45,6 +45,8 @@ enum : int {
   FR_S = 20,     // 10 slacks of the nonlinear rows: friction, 9 circle pairs (ego circle outer, obstacle circle inner)
   FR_A = 30,     // 25 A_k = d x_{k+1} / d x_k, row major
   FR_B = 55,     // 10 B_k = d x_{k+1} / d u_k, [t][c] at 2t + c
+  FR_ACL = 30,   // 30 closed loop [A + BK | d + B kff], entry (i, j) at 6i + j: written by the backward sweep OVER A_k | B_k once
+                 //    the stage has consumed them (nothing reads A_k / B_k after the sweep; the next linearisation rewrites them)
   FR_D = 65,     // 5  defect d_k = c(z_k) - x_{k+1}
   FR_ZERO = 70,  // 1  constant 0
   FR_H = 71,     // 9  Hessian of the x_k terms: h00 h01 h04 h11 h14 h44 h22 h23 h33
@@ -53,15 +55,16 @@ enum : int {
   FR_RG = 87,    // 2  input gradient
   FR_SX = 89,    // 2  cross terms d2 / d aLong d(delta, v) of the friction row
   FR_KK = 91,    // 12 gains K0[0..4] k0 K1[0..4] k1
-  FR_ACL = 103,  // 30 closed loop [A + BK | d + B kff], entry (i, j) at 6i + j
-  FR_DX = 133,   // 5  step dx_k
-  FR_DU = 138,   // 2  step du_k
-  FR_FAR = 140,  // 1  circle rows of x_k screened out this iteration
-  FR_LC = 141,   // 5  multiplier-weighted gradient of the x_k terms (adjoint recursion of the dynamics-curvature term)
-  FR_BV = 146,   // 6  multipliers of the road-boundary rows: left boundary x (centre, front, rear circle), right boundary x (...)
-  FR_BS = 152,   // 6  their slacks
-  FREC = 159     // odd: lane = stage accesses are bank-conflict free
+  FR_DX = 103,   // 5  step dx_k
+  FR_DU = 108,   // 2  step du_k
+  FR_FAR = 110,  // 1  circle rows of x_k screened out this iteration
+  FR_LC = 111,   // 5  multiplier-weighted gradient of the x_k terms (adjoint recursion of the dynamics-curvature term)
+  FREC_PLAIN = 117,  // record stride without the road-boundary rows (116 words + 1: odd strides keep lane = stage accesses bank-conflict free)
+  FR_BV = 116,   // 6  multipliers of the road-boundary rows: left boundary x (centre, front, rear circle), right boundary x (...)
+  FR_BS = 122,   // 6  their slacks
+  FREC_RB = 129  // record stride with them
 };
+MPC_HD constexpr int forces_rec_stride(bool rb) { return rb ? FREC_RB : FREC_PLAIN; }
 // state record k = 0..N-1
 enum : int {
   FS_XR = 0,     // 5 reference of the stage cost [path_x, path_y, 0, v_des, psi_ref] (positions relative to xinit)
@@ -77,7 +80,9 @@ enum : int { FH00 = 0, FH01, FH04, FH11, FH14, FH44, FH22, FH23, FH33 };
 struct FLayout {
   int N, o_state, o_rec, o_misc, words;
   // o_misc: 2 words, the position of xinit (the slab's positions are relative to it; the road boundaries are absolute)
-  MPC_HD explicit FLayout(int N_) : N(N_) { o_state = 0; o_rec = FST * N; o_misc = o_rec + FREC * N; words = (o_misc + 2 + 3) & ~3; }
+  MPC_HD explicit FLayout(int N_, bool rb = false) : N(N_) {
+    o_state = 0; o_rec = FST * N; o_misc = o_rec + forces_rec_stride(rb) * N; words = (o_misc + 2 + 3) & ~3;
+  }
 };
 
 // road boundaries (optional rows): vertex lists [n][2] in absolute coordinates, device memory
@@ -143,6 +148,7 @@ struct ForcesSolver {
   const ParamsT<T>& P;
   const T* Pt;
   const RoadBounds<T> rb;
+  static constexpr int FREC = RB ? FREC_RB : FREC_PLAIN;
   const FLayout L;
   const SlabRef<T> sl;
   const WarpCtx& w;
@@ -152,7 +158,7 @@ struct ForcesSolver {
   const T a2max, r2, irows;
 
   MPC_HD ForcesSolver(const FParams<T>& fp, const SlabRef<T>& slab, const WarpCtx& w_, const RoadBounds<T>& rb_ = RoadBounds<T>{nullptr, nullptr, 0, 0, T(0)})
-      : P(fp.P), Pt(fp.Pt), rb(rb_), L(fp.P.N), sl(slab), w(w_), lane(w_.lane()), tb(w_.lane()), a2max(fp.P.a_max * fp.P.a_max),
+      : P(fp.P), Pt(fp.Pt), rb(rb_), L(fp.P.N, RB), sl(slab), w(w_), lane(w_.lane()), tb(w_.lane()), a2max(fp.P.a_max * fp.P.a_max),
         r2(fp.P.r_sum * fp.P.r_sum), irows(T(1) / T(18 * fp.P.N - 13 + (RB ? 6 * (fp.P.N - 1) : 0))) {
     FC.dt = P.dt; FC.l_wb = P.l_wb; FC.l_fric = P.l_fric; FC.ego_off = P.ego_off;
     for (int q = 0; q < 5; ++q) { FC.Q[q] = P.Q[q]; FC.Pt[q] = fp.Pt[q]; }
@@ -539,14 +545,18 @@ struct ForcesSolver {
       }
       const T Pn = Fxx + F0i * T0 + F1i * T1;
       if (lane < 6) { sl[o + FR_KK + tb.j] = T0; sl[o + FR_KK + 6 + tb.j] = T1; }
-      if (lane < 30) sl[o + FR_ACL + lane] = sl[o + tb.aij] + sl[o + tb.bi0] * T0 + sl[o + tb.bi1] * T1;
+      const T acl = sl[o + tb.aij] + sl[o + tb.bi0] * T0 + sl[o + tb.bi1] * T1;
+      w.sync();                                   // every lane has read its A_k | B_k words: the closed-loop block may overwrite them
+      if (lane < 30) sl[o + FR_ACL + lane] = acl;
       Pij = Pn;
     }
     w.sync();
     return pd;
   }
-  MPC_HD void backward() const {
-    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; }
+  // A sweep overwrites A_k | B_k with the closed-loop block, so the Gauss-Newton fallback after a rejected curvature sweep
+  // linearises again first (rare path).
+  MPC_HD void backward(const ProbState<T>& st) const {
+    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; linearize(st); }
     backward_t<false>();
   }
 
@@ -893,7 +903,7 @@ struct ForcesSolver {
   MPC_HD void iterate(ProbState<T>& st) const {
     if (st.done) return;
     linearize(st);
-    backward();
+    backward(st);
     forward_sweep();
     FwdOut f = forward_stats(st);
     if (!m_finite(f.step_inf) || !m_finite(f.dphi)) { st.status = ST_NAN; st.done = 1; return; }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_forces_solve_kernel(const __grid
   __shared__ __align__(8) uint64_t bar_p[WPC];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.fp.P.N;
-  const FLayout L(N);
+  const FLayout L(N, RB);
   const int total_warps = gridDim.x * WPC;
   double* const stg = reinterpret_cast<double*>(smem_raw + (size_t)WPC * L.words * sizeof(T)) + (size_t)wid * 10 * N;
   if (threadIdx.x == 0) {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(32 * WPC) mpc_forces_closed_loop_kernel(const 
   unsigned char* const smem_raw = mpc_dyn_smem;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.fp.P.N, Tlen = a.Tlen;
-  const FLayout L(N);
+  const FLayout L(N, RB);
   const int total_warps = gridDim.x * WPC;
   double* const par = reinterpret_cast<double*>(smem_raw + (size_t)WPC * L.words * sizeof(T)) + (size_t)wid * (17 * N + 6);
   double* const Zw = par + 10 * N;
@@ -191,20 +191,12 @@ __global__ void __launch_bounds__(32 * WPC) mpc_forces_closed_loop_kernel(const 
 }
 
 template <typename T>
-static cudaError_t plan_forces(KernelPlan& k, int optin, int sms) {
-  // one grid shape for the kernels with and without the road-boundary rows
-  int c0 = 0, c1 = 0;
-  cudaError_t e;
-  if (k.wpc == 2) {
-    e = plan_kernel(mpc_forces_solve_kernel<T, 2, false>, 2, k.smem, optin, sms, &c0);
-    if (e == cudaSuccess) e = plan_kernel(mpc_forces_solve_kernel<T, 2, true>, 2, k.smem, optin, sms, &c1);
-  } else {
-    k.wpc = 1;
-    e = plan_kernel(mpc_forces_solve_kernel<T, 1, false>, 1, k.smem, optin, sms, &c0);
-    if (e == cudaSuccess) e = plan_kernel(mpc_forces_solve_kernel<T, 1, true>, 1, k.smem, optin, sms, &c1);
-  }
-  k.max_ctas = c0 < c1 ? c0 : c1;
-  return e;
+static cudaError_t plan_forces(KernelPlan& k, bool rb, int optin, int sms) {
+  if (k.wpc == 2) return rb ? plan_kernel(mpc_forces_solve_kernel<T, 2, true>, 2, k.smem, optin, sms, &k.max_ctas)
+                            : plan_kernel(mpc_forces_solve_kernel<T, 2, false>, 2, k.smem, optin, sms, &k.max_ctas);
+  k.wpc = 1;
+  return rb ? plan_kernel(mpc_forces_solve_kernel<T, 1, true>, 1, k.smem, optin, sms, &k.max_ctas)
+            : plan_kernel(mpc_forces_solve_kernel<T, 1, false>, 1, k.smem, optin, sms, &k.max_ctas);
 }
 template <typename T>
 static cudaError_t launch_forces(mpcb200_handle* h, ForcesArgs<T>& a, cudaStream_t s, const KernelPlan& k, int nwork) {
@@ -233,6 +225,9 @@ static void fill_forces_args(mpcb200_handle* h, ForcesArgs<T>& a, const double* 
   a.rb.left = base; a.rb.right = base ? base + 2 * nl : nullptr;
   a.rb.nl = base ? (int)nl : 0; a.rb.nr = base ? (int)nr : 0; a.rb.r_min = (T)h->rb_rmin;
 }
+// launch shapes of the kernel without (v = 0) and with (v = 1) the road-boundary rows: their slabs differ (FLayout), so do the
+// shared-memory sizes and the resident grids.  One problem per CTA unless cfg.warps_per_cta asks for two: shared memory binds the
+// residency (11 problems per SM at N = 30 in float32), and single-warp CTAs pack it without a remainder.
 static int ensure_forces_plan(mpcb200_handle* h) {
   if (h->forces_planned) return 0;
   cudaDeviceProp prop;
@@ -240,24 +235,25 @@ static int ensure_forces_plan(mpcb200_handle* h) {
   const int optin = (int)prop.sharedMemPerBlockOptin, sms = prop.multiProcessorCount;
   const size_t smem_max = prop.sharedMemPerBlockOptin;
   const bool f64 = h->cfg.precision == MPCB200_F64;
-  const FLayout L(h->cfg.N);
-  const int pref = (h->cfg.warps_per_cta == 1) ? 1 : 2;
-  const int cand[2] = {pref, 1};
-  bool fits = false;
-  for (int i = 0; i < 2 && !fits; ++i) {
-    const size_t need = forces_smem_bytes_for(h->cfg.N, L.words, h->elem, cand[i]);
-    if (need + 1024 <= smem_max) { h->forces.wpc = cand[i]; h->forces.smem = need; fits = true; }
-  }
-  if (!fits) { h->err = "horizon too long: the FORCESPRO-formulation KKT slab does not fit shared memory"; return -2; }
-  cudaError_t e = f64 ? plan_forces<double>(h->forces, optin, sms) : plan_forces<float>(h->forces, optin, sms);
-  if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO formulation)", e);
-  h->forces_refine.wpc = 0;
-  if (!f64 && h->cfg.refine_f64 && h->q_list) {
-    h->forces_refine.wpc = 1; h->forces_refine.smem = forces_smem_bytes_for(h->cfg.N, L.words, 8, 1);
-    if (h->forces_refine.smem + 1024 > smem_max) { h->err = "horizon too long for the float64 refinement pass (FORCESPRO formulation)"; return -2; }
-    e = plan_forces<double>(h->forces_refine, optin, sms);
-    if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO formulation, float64 refinement)", e);
-    if (h->forces_refine.max_ctas > sms) h->forces_refine.max_ctas = sms;
+  for (int v = 0; v < 2; ++v) {
+    const FLayout L(h->cfg.N, v == 1);
+    const int cand[2] = {h->cfg.warps_per_cta == 2 ? 2 : 1, 1};
+    bool fits = false;
+    for (int i = 0; i < 2 && !fits; ++i) {
+      const size_t need = forces_smem_bytes_for(h->cfg.N, L.words, h->elem, cand[i]);
+      if (need + 1024 <= smem_max) { h->forces[v].wpc = cand[i]; h->forces[v].smem = need; fits = true; }
+    }
+    if (!fits) { h->err = "horizon too long: the FORCESPRO-formulation KKT slab does not fit shared memory"; return -2; }
+    cudaError_t e = f64 ? plan_forces<double>(h->forces[v], v == 1, optin, sms) : plan_forces<float>(h->forces[v], v == 1, optin, sms);
+    if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO formulation)", e);
+    h->forces_refine[v].wpc = 0;
+    if (!f64 && h->cfg.refine_f64 && h->q_list) {
+      h->forces_refine[v].wpc = 1; h->forces_refine[v].smem = forces_smem_bytes_for(h->cfg.N, L.words, 8, 1);
+      if (h->forces_refine[v].smem + 1024 > smem_max) { h->err = "horizon too long for the float64 refinement pass (FORCESPRO formulation)"; return -2; }
+      e = plan_forces<double>(h->forces_refine[v], v == 1, optin, sms);
+      if (e != cudaSuccess) return fail(h, "kernel configuration (FORCESPRO formulation, float64 refinement)", e);
+      if (h->forces_refine[v].max_ctas > sms) h->forces_refine[v].max_ctas = sms;
+    }
   }
   h->forces_planned = 1;
   return 0;
@@ -269,12 +265,12 @@ static int forces_closed_loop_t(mpcb200_handle* h, const double* wt, int32_t Tle
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h->cfg.device));
   const int optin = (int)prop.sharedMemPerBlockOptin, sms = prop.multiProcessorCount;
-  const FLayout L(h->cfg.N);
-  const size_t smem = forces_loop_smem_bytes_for(h->cfg.N, L.words, sizeof(T), 1);
-  if (smem + 1024 > prop.sharedMemPerBlockOptin) { h->err = "horizon too long for the FORCESPRO-formulation closed loop"; return -2; }
   ForcesLoopArgs<T> a;
   ForcesArgs<T> tmp; fill_forces_args(h, tmp, wt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B);
   a.fp = tmp.fp; a.rb = tmp.rb;
+  const FLayout L(h->cfg.N, a.rb.nl > 0 && a.rb.nr > 0);
+  const size_t smem = forces_loop_smem_bytes_for(h->cfg.N, L.words, sizeof(T), 1);
+  if (smem + 1024 > prop.sharedMemPerBlockOptin) { h->err = "horizon too long for the FORCESPRO-formulation closed loop"; return -2; }
   for (int i = 0; i < 6; ++i) a.obstacle[i] = h->cfg.obstacle[i];
   a.path = d_path; a.orient = d_orient; a.vel = d_vel; a.x0 = d_x0; a.traj = d_traj; a.ctrl = d_ctrl; a.status = d_status; a.iters = d_iters;
   a.ctr = h->ctr; a.l_wb = h->cfg.l_wb; a.dt = h->cfg.dt; a.B = B; a.Tlen = Tlen;
@@ -330,18 +326,19 @@ int mpcb200_forces_solve(mpcb200_handle* h, const double* weights_terminal, cons
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e;
+  const int v = (h->rb_f64 && h->rb_nl > 0 && h->rb_nr > 0) ? 1 : 0;
   if (h->cfg.precision == MPCB200_F64) {
     ForcesArgs<double> a; fill_forces_args(h, a, weights_terminal, d_xinit, d_params, d_z_init, d_z, d_status, d_iters, B);
-    e = launch_forces<double>(h, a, s, h->forces, B);
+    e = launch_forces<double>(h, a, s, h->forces[v], B);
   } else {
-    const bool refine = h->cfg.refine_f64 && d_status && h->forces_refine.wpc;
+    const bool refine = h->cfg.refine_f64 && d_status && h->forces_refine[v].wpc;
     ForcesArgs<float> a; fill_forces_args(h, a, weights_terminal, d_xinit, d_params, d_z_init, d_z, d_status, d_iters, B);
     a.q_list = refine ? h->q_list : nullptr; a.pdl_primary = refine ? 1 : 0;
-    e = launch_forces<float>(h, a, s, h->forces, B);
+    e = launch_forces<float>(h, a, s, h->forces[v], B);
     if (e == cudaSuccess && refine) {
       ForcesArgs<double> r; fill_forces_args(h, r, weights_terminal, d_xinit, d_params, d_z_init, d_z, d_status, d_iters, B);
       r.q_list = h->q_list; r.refine = 1;
-      e = launch_forces<double>(h, r, s, h->forces_refine, B);
+      e = launch_forces<double>(h, r, s, h->forces_refine[v], B);
     }
   }
   if (e != cudaSuccess) return fail(h, "mpc_forces_solve_kernel launch", e);

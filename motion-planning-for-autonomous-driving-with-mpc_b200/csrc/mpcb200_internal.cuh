@@ -71,7 +71,7 @@ struct mpcb200_handle {
   mpcb200_scenario* scn_table;   // device copy of the scenario table (mpcb200_set_scenarios)
   int n_scn;
   KernelPlan scn, scn_refine;    // launch shapes of the per-problem-scenario kernels (planned at set_scenarios)
-  KernelPlan forces, forces_refine;   // FORCESPRO-formulation kernels (planned at the first mpcb200_forces_solve)
+  KernelPlan forces[2], forces_refine[2];   // FORCESPRO-formulation kernels without / with the road-boundary rows (planned at the first mpcb200_forces_solve)
   int forces_planned;
   void *rb_f32, *rb_f64;              // road-boundary vertex lists on the device, [left | right], both precisions (mpcb200_forces_set_road_boundaries)
   int rb_nl, rb_nr;

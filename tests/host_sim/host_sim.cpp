@@ -135,7 +135,7 @@ static void run_forces(const mpcb200_config& cfg, const double* Pt, const double
                        int* status, int* iters, int B, int trace, const double* bl = nullptr, int nl = 0, const double* br = nullptr, int nr = 0,
                        double rmin = 0.0) {
   const int N = cfg.N;
-  FLayout L(N);
+  FLayout L(N, nl > 0 && nr > 0);
   std::vector<T> buf(L.words + 4);
   std::vector<T> bnd(2 * (size_t)(nl + nr) + 2);
   for (int i = 0; i < 2 * nl; ++i) bnd[i] = (T)bl[i];
