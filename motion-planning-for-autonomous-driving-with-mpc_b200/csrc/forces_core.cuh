@@ -45,8 +45,6 @@ enum : int {
   FR_S = 20,     // 10 slacks of the nonlinear rows: friction, 9 circle pairs (ego circle outer, obstacle circle inner)
   FR_A = 30,     // 25 A_k = d x_{k+1} / d x_k, row major
   FR_B = 55,     // 10 B_k = d x_{k+1} / d u_k, [t][c] at 2t + c
-  FR_ACL = 30,   // 30 closed loop [A + BK | d + B kff], entry (i, j) at 6i + j: written by the backward sweep OVER A_k | B_k once
-                 //    the stage has consumed them (nothing reads A_k / B_k after the sweep; the next linearisation rewrites them)
   FR_D = 65,     // 5  defect d_k = c(z_k) - x_{k+1}
   FR_ZERO = 70,  // 1  constant 0
   FR_H = 71,     // 9  Hessian of the x_k terms: h00 h01 h04 h11 h14 h44 h22 h23 h33
@@ -55,14 +53,17 @@ enum : int {
   FR_RG = 87,    // 2  input gradient
   FR_SX = 89,    // 2  cross terms d2 / d aLong d(delta, v) of the friction row
   FR_KK = 91,    // 12 gains K0[0..4] k0 K1[0..4] k1
-  FR_DX = 103,   // 5  step dx_k
-  FR_DU = 108,   // 2  step du_k
-  FR_FAR = 110,  // 1  circle rows of x_k screened out this iteration
-  FR_LC = 111,   // 5  multiplier-weighted gradient of the x_k terms (adjoint recursion of the dynamics-curvature term)
-  FREC_PLAIN = 117,  // record stride without the road-boundary rows (116 words + 1: odd strides keep lane = stage accesses bank-conflict free)
-  FR_BV = 116,   // 6  multipliers of the road-boundary rows: left boundary x (centre, front, rear circle), right boundary x (...)
-  FR_BS = 122,   // 6  their slacks
-  FREC_RB = 129  // record stride with them
+  FR_ACL = 103,  // 30 closed loop [A + BK | d + B kff], entry (i, j) at 6i + j.  (Aliasing it onto A_k | B_k -- 11 instead of 9
+                 //    problems per SM -- was measured: no gain at large batches, and the Gauss-Newton fallback after a rejected
+                 //    curvature sweep then has to linearise again: USA_Lanker -22 %.  Kept separate.)
+  FR_DX = 133,   // 5  step dx_k
+  FR_DU = 138,   // 2  step du_k
+  FR_FAR = 140,  // 1  circle rows of x_k screened out this iteration
+  FR_LC = 141,   // 5  multiplier-weighted gradient of the x_k terms (adjoint recursion of the dynamics-curvature term)
+  FREC_PLAIN = 147,  // record stride without the road-boundary rows (odd strides keep lane = stage accesses bank-conflict free)
+  FR_BV = 146,   // 6  multipliers of the road-boundary rows: left boundary x (centre, front, rear circle), right boundary x (...)
+  FR_BS = 152,   // 6  their slacks
+  FREC_RB = 159  // record stride with them
 };
 MPC_HD constexpr int forces_rec_stride(bool rb) { return rb ? FREC_RB : FREC_PLAIN; }
 // state record k = 0..N-1
@@ -545,18 +546,14 @@ struct ForcesSolver {
       }
       const T Pn = Fxx + F0i * T0 + F1i * T1;
       if (lane < 6) { sl[o + FR_KK + tb.j] = T0; sl[o + FR_KK + 6 + tb.j] = T1; }
-      const T acl = sl[o + tb.aij] + sl[o + tb.bi0] * T0 + sl[o + tb.bi1] * T1;
-      w.sync();                                   // every lane has read its A_k | B_k words: the closed-loop block may overwrite them
-      if (lane < 30) sl[o + FR_ACL + lane] = acl;
+      if (lane < 30) sl[o + FR_ACL + lane] = sl[o + tb.aij] + sl[o + tb.bi0] * T0 + sl[o + tb.bi1] * T1;
       Pij = Pn;
     }
     w.sync();
     return pd;
   }
-  // A sweep overwrites A_k | B_k with the closed-loop block, so the Gauss-Newton fallback after a rejected curvature sweep
-  // linearises again first (rare path).
-  MPC_HD void backward(const ProbState<T>& st) const {
-    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; linearize(st); }
+  MPC_HD void backward() const {
+    if (P.hessian == HESS_EXACT) { if (backward_t<true>()) return; }
     backward_t<false>();
   }
 
@@ -903,7 +900,7 @@ struct ForcesSolver {
   MPC_HD void iterate(ProbState<T>& st) const {
     if (st.done) return;
     linearize(st);
-    backward(st);
+    backward();
     forward_sweep();
     FwdOut f = forward_stats(st);
     if (!m_finite(f.step_inf) || !m_finite(f.dphi)) { st.status = ST_NAN; st.done = 1; return; }
