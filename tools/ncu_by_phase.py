@@ -12,13 +12,19 @@ it0 = next(i for i, l in enumerate(src) if "void iterate(" in l) + 1
 it1 = len(src)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l and l.rstrip().endswith(":"))
+dis = start = None
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):       # one cubin per translation unit: take the one that holds the kernel
+    d = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    st = next((i for i, l in enumerate(d) if l.startswith(".text.") and kern in l and l.rstrip().endswith(":")), None)
+    if st is not None:
+        dis, start = d, st
+        break
+if dis is None:
+    sys.exit(f"kernel {kern} not found in {so}")
 info = {}
 chain = []; fresh = True
 for l in dis[start + 1:]:
-    if l.startswith("//---------------------"):
+    if l.startswith("//---------------------") or l.startswith(".text."):
         break
     if "//## File" in l:
         if fresh: chain = []; fresh = False
