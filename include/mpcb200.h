@@ -79,7 +79,9 @@ typedef struct mpcb200_config {
   double kappa_warm;               /* dual warm start: carried multipliers are kept within [mu_warm/(kappa s), kappa mu_warm/s] */
   double stiff_slack;              /* float32: an acceptable-level exit while a live obstacle row has a slack below this is reported as status 3 (refined in float64 when refine_f64 is set) */
   int32_t warm_duals;              /* mpcb200_closed_loop: 1 = carry slacks / multipliers across MPC steps (shifted one stage), 0 = IPOPT-like restart every step */
-  int32_t warps_per_cta;           /* problems (= warps) per CTA: 0 = library default, else 1 | 2 | 4 */
+  int32_t warps_per_cta;           /* problems (= warps) per CTA: 0 = library default, else 1 | 2 | 4; 8 | 16: the phase-aligned kernel
+                                      (one CTA barrier per SQP iteration, csrc/aligned_solver.cu; float32 Gauss-Newton fused solves only,
+                                      bit-identical results, measured no faster: profiles/r02_summary.md section 12) */
   int32_t host_route;              /* mpcb200_solve_host: 0 = zero-copy when every buffer is pinned, else staged; 1 = always staged */
   int32_t host_chunks;             /* staged host route: chunks of the copy / solve / copy pipeline, 0 = by batch size */
 } mpcb200_config;

@@ -19,75 +19,6 @@
 #include "loop_core.cuh"
 #include "forces_model.cuh"
 
-// ===================================================================================================== kernel args
-enum : int { MODE_ONESHOT = 0, MODE_BEGIN = 1, MODE_ITER = 2, MODE_END = 3 };
-
-template <typename T>
-struct SolveArgs {
-  ParamsT<T> P;
-  double obstacle[6];
-  const double* xref;   // [B][N+1][5]
-  double* X;            // [B][N+1][5]  optimal states out
-  double* U;            // [B][N][2]    optimal controls out
-  const double* Xin;    // warm start in (may alias X / U)
-  const double* Uin;
-  int* status;          // [B]
-  int* iters;           // [B]
-  double* lam;          // [B][14N+2] inequality multipliers / obstacle slacks in and out (mpcb200_solve_dual), or null
-  T* slab;              // global image of the slabs [B][words] (stepwise mode)
-  ProbState<T>* state;  // [B] (stepwise mode)
-  T* obs_shift;         // [B][6] shifted obstacle centres (stepwise mode)
-  WorkCtr* ctr;         // work counters (dynamic scheduling beyond the first wave, refinement queue)
-  int* q_list;          // [max_batch] refinement queue: written by the float32 pass, consumed by the float64 pass
-  int B;
-  int mode;
-  int n_iter;
-  int cold;             // 1: X / U are outputs only (cold start: X_0 tiled, zero controls)
-  int refine;           // 1: float64 refinement pass -- the work list is q_list[0 .. q_count), warm start = the float32 X / U
-  int dynamic;          // 1: B exceeds the launch's warps: warps claim further problems from ctr->next
-  int pdl_primary;      // 1: a dependent launch (the refinement pass) follows: let it get resident while this grid runs
-};
-
-// shared-memory carve-up of one CTA: [WPC slabs of T][WPC float64 xref staging blocks of (5(N+1) + 1 rounded up to even) doubles]
-// The staging block has one spare double in front: a row whose global address is 8 (mod 16) is placed 8 bytes in, so that the
-// 16-byte-aligned interior the TMA bulk copy moves is 16-byte aligned on both sides.
-MPC_HD int stg_doubles(int N) { return (5 * (N + 1) + 2) & ~1; }
-template <typename T, int WPC>
-struct Smem {
-  int nx, nu;
-  size_t slab_bytes;
-  unsigned char* raw;
-  __device__ Smem(unsigned char* raw_, int N, int words) : nx(5 * (N + 1)), nu(2 * N), slab_bytes((size_t)words * sizeof(T)), raw(raw_) {}
-  __device__ T* slab(int w) const { return reinterpret_cast<T*>(raw + (size_t)w * slab_bytes); }
-  __device__ double* xstg(int w) const { return reinterpret_cast<double*>(raw + (size_t)WPC * slab_bytes) + (size_t)w * stg_doubles(nu / 2); }
-};
-static size_t smem_bytes_for(int N, int words, size_t elem, int wpc) {
-  return (size_t)wpc * ((size_t)words * elem + (size_t)stg_doubles(N) * sizeof(double));
-}
-
-// One problem's xref block HBM (or pinned host memory) -> the warp's staging: the 16-byte-aligned interior by ONE TMA bulk copy
-// issued by lane 0 (completion on the warp's mbarrier), the 8-byte head / tail words a misaligned row leaves by plain loads.
-// Returns the staging address of the row.  Works for every 8-byte-aligned address (odd problem index at even N, sliced tensors).
-__device__ __forceinline__ const double* fetch_xref(const double* g, double* stg, int nx, uint64_t* bar, uint32_t& phase, int lane) {
-  const uint32_t head = (uint32_t)((uintptr_t)g & 8u);                 // 0 or 8 bytes in front of the aligned interior
-  const uint32_t bytes = (uint32_t)nx * 8u;
-  const uint32_t interior = (bytes - head) & ~15u;
-  double* row = stg + (head >> 3);
-  // the staging was last read through the generic proxy (previous problem): order those reads before the async-proxy write
-  fence_async_smem();
-  __syncwarp();
-  if (lane == 0) {
-    mbar_expect_tx(bar, interior);
-    tma_load_1d(reinterpret_cast<unsigned char*>(row) + head, reinterpret_cast<const unsigned char*>(g) + head, interior, bar);
-  }
-  if (lane == 1 && head) row[0] = g[0];
-  if (lane == 2 && head + interior < bytes) row[nx - 1] = g[nx - 1];
-  mbar_wait(bar, phase);
-  phase ^= 1u;
-  __syncwarp();
-  return row;
-}
-
 // resident warps per SM the float32 kernels are compiled for: 16 = 4 per sub-partition = 128 registers per thread at most (the
 // kernel needs ~120); 18-20 would need <= 96 registers (a sub-partition then holds 5 warps) and spills
 #ifndef MPC_WARPS_PER_SM
@@ -485,7 +416,11 @@ static int do_solve(mpcb200_handle* h, int mode, int n_iter, const double* xref,
   // a float32 handle with cfg.refine_f64 queues what it did not converge for the float64 pass that follows (fused mode only)
   a.q_list = (mode == MODE_ONESHOT && sizeof(T) == 4 && h->cfg.refine_f64 && status) ? h->q_list : nullptr;
   a.B = B; a.mode = mode; a.n_iter = n_iter; a.cold = cold; a.refine = 0; a.dynamic = 0; a.pdl_primary = a.q_list ? 1 : 0;
-  cudaError_t e = dispatch_solve<T>(h, a, s, h->solve, B);
+  cudaError_t e;
+  // cfg.warps_per_cta = 8 | 16: the phase-aligned kernel (aligned_solver.cu) for fused float32 Gauss-Newton solves
+  if (sizeof(T) == 4 && mode == MODE_ONESHOT && !lam && a.P.hessian == HESS_GN && (h->cfg.warps_per_cta == 8 || h->cfg.warps_per_cta == 16))
+    e = launch_solve_aligned(h, reinterpret_cast<SolveArgs<float>&>(a), s, B);
+  else e = dispatch_solve<T>(h, a, s, h->solve, B);
   if (e != cudaSuccess) return fail(h, "mpc_warp_solve_kernel launch", e);
   return 0;
 }

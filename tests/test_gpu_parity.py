@@ -718,3 +718,28 @@ def test_per_problem_scenarios_one_launch_equals_per_scenario_launches():
     lf = sid != 0
     assert np.abs(U[lf] - Ur[lf]).max() < 1e-4 and np.abs(X[lf] - Xr[lf]).max() < 1e-4 and (it[lf] == itr[lf]).mean() > 0.97
     assert np.abs(U[~lf] - Ur[~lf]).max() < 1e-3 and np.abs(X[~lf] - Xr[~lf]).max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wpc", [8, 16])
+def test_phase_aligned_kernel_is_bitwise_the_fused_kernel(wpc):
+    """cfg.warps_per_cta = 8 | 16 selects mpc_warp_solve_aligned_kernel (one CTA barrier per SQP iteration, aligned_solver.cu): same
+    per-problem arithmetic as the independent-warp kernel, so the results are bit-identical -- ragged batch larger than the resident
+    grid (dynamic claiming), cold and warm start, and the collision-avoidance batch with the float64 refinement queue behind it."""
+    import mpc_b200
+    from mpc_b200.optimizer import B200Optimizer, make_configuration, init_values_from_state
+    for name, B, seed in (("ZAM_Over-1_1_LF", 5003, 20261017), ("ZAM_Over-1_1_CA", 1027, 20261018)):
+        sc, x0, xref, X, U = mpc_b200.make_batch(name, B, 30, seed)
+        ref = B200Optimizer(make_configuration(sc, 30), init_values_from_state(sc.x0), 30, precision="f32", max_batch=B)
+        alg = B200Optimizer(make_configuration(sc, 30), init_values_from_state(sc.x0), 30, precision="f32", max_batch=B, warps_per_cta=wpc)
+        U0, X0, s0, i0 = ref.solve_batch(xref)
+        U1, X1, s1, i1 = alg.solve_batch(xref)
+        assert torch_equal(U0, U1) and torch_equal(X0, X1) and torch_equal(s0, s1) and torch_equal(i0, i1)
+        U2, X2, s2, i2 = ref.solve_batch(xref, X0, U0)
+        U3, X3, s3, i3 = alg.solve_batch(xref, X0, U0)
+        assert torch_equal(U2, U3) and torch_equal(X2, X3) and torch_equal(s2, s3) and torch_equal(i2, i3)
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))
