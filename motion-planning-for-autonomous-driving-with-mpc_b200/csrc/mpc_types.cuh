@@ -56,6 +56,7 @@ struct ProbState {
   T kkt;              // last step inf-norm (diagnostic)
   T d_al, d_ap, d_ad, d_c1, d_dphi; int d_blk;   // diagnostics of the last iteration
   T best;             // smallest accepted step length*norm seen at mu_min (stall detection)
+  T pstep;            // full Newton step norm of the previous iteration if it was taken in full near mu_min, else 0 (final-phase rate estimate)
   int status, iters, done, nfail, nsoc, nacc, centered, nstall;
 };
 

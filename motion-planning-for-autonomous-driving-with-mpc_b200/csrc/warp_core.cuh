@@ -300,7 +300,7 @@ struct WarpSolver {
   // trig cache.  Every lane ends with the same (uniform) ProbState.
   MPC_HD void init(ProbState<T>& st) const {
     const int N = P.N;
-    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.nstall = 0; st.best = T(1e30); st.kkt = T(0);
+    st.mu = P.mu0; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.nstall = 0; st.best = T(1e30); st.kkt = T(0); st.pstep = T(0);
     st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
     const T de0 = xa(0, 2), v0 = xa(0, 3);
     const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
@@ -519,7 +519,7 @@ struct WarpSolver {
   // schedule restarts at mu_warm instead of mu0.  Every lane ends with the same (uniform) ProbState.
   MPC_HD void init_warm(ProbState<T>& st) const {
     const int N = P.N;
-    st.mu = P.mu_warm; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.nstall = 0; st.best = T(1e30); st.kkt = T(0);
+    st.mu = P.mu_warm; st.rho = T(1); st.status = ST_MAXIT; st.iters = 0; st.done = 0; st.nfail = 0; st.nsoc = 0; st.nacc = 0; st.centered = 0; st.nstall = 0; st.best = T(1e30); st.kkt = T(0); st.pstep = T(0);
     st.d_al = st.d_ap = st.d_ad = st.d_c1 = st.d_dphi = T(0); st.d_blk = 0;
     const T de0 = xa(0, 2), v0 = xa(0, 3);
     const T s0 = v0 * v0 * m_tan(de0) / P.l_fric;
@@ -827,7 +827,7 @@ struct WarpSolver {
   // ---------------------------------------------------------------- phase E: step-length limits, merit slope (lane = stage)
   // a_p / a_d hold, until the final reduction, the LARGEST relative decrease -ds/s and -dnu/nu over the rows; the
   // fraction-to-the-boundary step lengths are then min(1, tau / that) -- one division per iteration instead of per row.
-  struct FwdOut { T a_p, a_d, dphi, c1, step_inf, mag; int blk, cur; };
+  struct FwdOut { T a_p, a_d, lim, dphi, c1, step_inf, mag; int blk, cur; };
 
   MPC_HD void row_limits(T s, T nu, T ds, T mu, T tau, FwdOut& o) const {
     const T is = m_rcp(s), inu = m_rcp(nu);
@@ -899,6 +899,7 @@ struct WarpSolver {
       o.blk = code; }
 #endif
     o.a_p = w.max_nonneg(m_max(o.a_p, T(0))); o.a_d = w.max_nonneg(m_max(o.a_d, T(0)));
+    o.lim = tau * m_rcp(m_max(m_max(o.a_p, o.a_d), T(1e-3)));        // uncapped fraction-to-the-boundary length (primal and dual)
     o.a_p = (o.a_p > tau) ? tau * m_rcp(o.a_p) : T(1);
     o.a_d = (o.a_d > tau) ? tau * m_rcp(o.a_d) : T(1);
     o.step_inf = w.max_nonneg(fin ? o.step_inf : T(0));
@@ -1134,6 +1135,22 @@ struct WarpSolver {
   }
 
   // ---------------------------------------------------------------- one SQP / interior-point iteration (uniform control flow)
+  MPC_HD static bool tune_extrap() {
+#if !defined(__CUDACC__) && defined(MPC_DIAG)
+    static const bool v = getenv("MPC_EXTRAP") ? atoi(getenv("MPC_EXTRAP")) != 0 : true;
+    return v;
+#else
+    return true;
+#endif
+  }
+  MPC_HD static bool tune_pred() {
+#if !defined(__CUDACC__) && defined(MPC_DIAG)
+    static const bool v = getenv("MPC_PRED") ? atoi(getenv("MPC_PRED")) != 0 : true;
+    return v;
+#else
+    return true;
+#endif
+  }
   MPC_HD void iterate(ProbState<T>& st) const {
     if (st.done) return;
     linearize(st);
@@ -1152,6 +1169,16 @@ struct WarpSolver {
     const T cfloor = T(8) * epsm * f.mag;                       // rounding-noise floor of the l1 infeasibility
     const bool trust = (f.c1 <= cfloor) && (f.step_inf <= P.trust_step);
     T al = f.a_p;
+    // Final-phase extrapolation.  On a weakly active row (slack and multiplier both -> 0) Newton's step on s nu = mu HALVES per
+    // iteration -- a double root; twice the Newton step restores fast convergence.  Detected from two scalars (this full step is
+    // 0.4 .. 0.6 of the previous full step, both at the final barrier parameter); the doubled length is the first line-search
+    // trial (Armijo as usual, the plain Newton step is the second), capped by the uncapped fraction-to-the-boundary length.
+    T ad = f.a_d;
+    bool extrap = false;
+    if (tune_extrap() && st.pstep > T(0) && st.mu <= P.mu_min * T(1.0001) && f.a_p >= T(1) && f.a_d >= T(1) &&
+        f.step_inf > T(0.4) * st.pstep && f.step_inf < T(0.6) * st.pstep && f.lim > T(1.5)) {
+      al = m_min(T(2), f.lim); extrap = true;
+    }
     bool accepted = false;
     for (int t = 0; t < P.ls_max; ++t) {
       T dphi, c1, nz;
@@ -1187,12 +1214,22 @@ struct WarpSolver {
       st.nfail = 0;
     }
     T avg, cmax, smin_ob;
-    commit(st, al, f.a_d, avg, cmax, smin_ob);
+    if (extrap && al > T(1)) ad = al;                       // the multipliers take the same extrapolated length
+    commit(st, al, ad, avg, cmax, smin_ob);
     st.d_al = al; st.d_ap = f.a_p; st.d_ad = f.a_d; st.d_c1 = f.c1; st.d_dphi = f.dphi; st.d_blk = f.blk;
     st.iters++;
     st.kkt = f.step_inf;
+    // rate estimate for the next iteration: this full Newton step's norm if it was taken as it is near the final barrier
+    // parameter (an extrapolated or damped step says nothing about the rate)
+    const T pstep_new = (al == T(1) && st.mu <= T(2) * P.mu_min) ? f.step_inf : T(0);
     if (st.mu <= P.mu_min * T(1.0001) && f.c1 <= P.tol_feas) {
       if (al >= T(0.5) && al * f.step_inf <= P.tol_step) { st.status = ST_OPTIMAL; st.done = 1; return; }
+      // rate-based exit: two full steps in a row near the final barrier parameter shrinking at rate r = step / previous step <
+      // 0.5 leave a remaining error of about step r / (1 - r); below tol_step the next iteration would only confirm it
+      // (not in float32 with a stiff live obstacle row: there the step sizes are at the rounding-noise floor of the KKT solve and
+      // say nothing about the distance to the optimum -- measured: 8 of the 4096 config-3 instances ended 1.1e-3 .. 2.7e-3 off)
+      if (tune_pred() && al >= T(1) && st.pstep > T(0) && f.step_inf < T(0.5) * st.pstep && (sizeof(T) == 8 || smin_ob >= P.stiff_slack) &&
+          f.step_inf * f.step_inf <= P.tol_step * (st.pstep - f.step_inf)) { st.status = ST_OPTIMAL; st.done = 1; return; }
       // "acceptable" exit (IPOPT's acceptable_tol / acceptable_iter idea): with strongly active rows the barrier
       // weights reach 1/mu_min and the Newton step has a rounding-noise floor above tol_step; a run of steps at that
       // floor is convergence, not progress
@@ -1209,6 +1246,7 @@ struct WarpSolver {
       if (sz < T(0.5) * st.best) { st.best = sz; st.nstall = 0; }
       else if (++st.nstall >= P.stall_iters) { st.status = ST_STALLED; st.done = 1; return; }
     }
+    st.pstep = pstep_new;
     // Barrier warm-up: while no step of length >= 0.5 has been taken, a step blocked hard by the fraction-to-the-boundary
     // rule (alpha < mu_up_alpha) means the barrier is invisible next to the cost gradient -- the iteration would crawl
     // one bound per step.  Raise mu (and the multipliers with it, keeping s*nu on the central path) instead.
