@@ -173,3 +173,21 @@ def test_dual_block_round_trip_warm_starts_the_solve(name, N):
     assert (stc[ok] == 1).all()
     assert np.abs(Uc - Ub)[ok].max() < 1e-5 and np.abs(Xc - Xb)[ok].max() < 1e-5
     assert itc[ok].mean() <= 9.0 and (itc[ok] < itb[ok]).all()          # float64: mu_warm = 1e-4 -> 1e-9 alone takes ~5 reductions
+
+
+def test_final_phase_extrapolation_cuts_the_halving_tail():
+    """Problem 948 of the bench batch (BASELINE configs[1], seed 20261017): a weakly active stage-0 row makes Newton's step halve
+    per iteration at the final barrier parameter (11 iterations before the rule).  The doubled step on the detected halving
+    sequence + the rate-based exit bring it to <= 8; the solution still equals the float64 oracle within the stated tolerance, and
+    over the first 128 instances nothing needs more than 10 iterations."""
+    from oracle import nlp, ipm
+    sc, x0, xref, X, U = mpc_b200.make_batch("ZAM_Over-1_1_LF", 1024, 30, 20261017)
+    cfg = _cfg(sc, 30, 0)
+    Xs, Us, st, it, _ = hostsim.solve(cfg, xref[948:949], X[948:949], U[948:949])
+    assert st[0] == 1 and it[0] <= 8, (st, it)
+    d = nlp.make_nlp(30, sc.dt, sc.weights_setting, xref[948], sc.static_obstacle)
+    r = ipm.solve(d, nlp.pack(U[948], X[948]))
+    Uo, Xo = nlp.split(r["w"], 30)
+    assert r["status"] == 1 and np.abs(Us[0] - Uo).max() < 1e-3 and np.abs(Xs[0] - Xo).max() < 1e-3
+    _, _, st, it, _ = hostsim.solve(cfg, xref[:128], X[:128], U[:128])
+    assert (st == 1).all() and it.max() <= 10 and it.mean() < 5.4
