@@ -1135,6 +1135,22 @@ struct WarpSolver {
   }
 
   // ---------------------------------------------------------------- one SQP / interior-point iteration (uniform control flow)
+  // remaining error after this step, from the contraction r = step / previous step of the last two full steps: the next
+  // ratio is taken as r^1.5 (Newton-like iterations square it, Gauss-Newton's linear rate keeps it: 1.5 sits between), the tail as
+  // a geometric series in that ratio
+  MPC_HD bool rate_ok(T step, T prev) const {
+    const T r = step * m_rcp(prev);
+    const T q = rate_pow() ? r * m_sqrt_fast(r) : r;
+    return step * q <= P.tol_step * (T(1) - q);
+  }
+  MPC_HD static bool rate_pow() {
+#if !defined(__CUDACC__) && defined(MPC_DIAG)
+    static const bool v = getenv("MPC_RATEPOW") ? atoi(getenv("MPC_RATEPOW")) != 0 : true;
+    return v;
+#else
+    return true;
+#endif
+  }
   MPC_HD static bool tune_extrap() {
 #if !defined(__CUDACC__) && defined(MPC_DIAG)
     static const bool v = getenv("MPC_EXTRAP") ? atoi(getenv("MPC_EXTRAP")) != 0 : true;
@@ -1229,7 +1245,7 @@ struct WarpSolver {
       // (not in float32 with a stiff live obstacle row: there the step sizes are at the rounding-noise floor of the KKT solve and
       // say nothing about the distance to the optimum -- measured: 8 of the 4096 config-3 instances ended 1.1e-3 .. 2.7e-3 off)
       if (tune_pred() && al >= T(1) && st.pstep > T(0) && f.step_inf < T(0.5) * st.pstep && (sizeof(T) == 8 || smin_ob >= P.stiff_slack) &&
-          f.step_inf * f.step_inf <= P.tol_step * (st.pstep - f.step_inf)) { st.status = ST_OPTIMAL; st.done = 1; return; }
+          rate_ok(f.step_inf, st.pstep)) { st.status = ST_OPTIMAL; st.done = 1; return; }
       // "acceptable" exit (IPOPT's acceptable_tol / acceptable_iter idea): with strongly active rows the barrier
       // weights reach 1/mu_min and the Newton step has a rounding-noise floor above tol_step; a run of steps at that
       // floor is convergence, not progress
